@@ -1,0 +1,49 @@
+import gzip, hashlib, io, json, os, sys, tarfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run under gpurun)")
+
+
+_FIXTURES = None
+
+
+def load_fixtures():
+    """name -> bytes for every file of the reference's tests/data and tests/specimen (bundled)."""
+    global _FIXTURES
+    if _FIXTURES is None:
+        out = {}
+        with tarfile.open(os.path.join(GOLDEN, "ref_fixtures.tar.gz"), "r:gz") as tf:
+            for m in tf.getmembers():
+                out[m.name] = tf.extractfile(m).read()
+        _FIXTURES = out
+    return _FIXTURES
+
+
+@pytest.fixture(scope="session")
+def fixtures():
+    return load_fixtures()
+
+
+def parse_specimen_index(text):
+    """Minimal reader for tests/specimen/*/index.toml: [[valid]]/[[invalid]] tables with
+    filename = "..." and optional tags = [..] (ref: tests/format_specimens.rs:7-19)."""
+    out = {"valid": [], "invalid": []}
+    cur = None
+    for line in text.splitlines():
+        s = line.strip()
+        if s in ("[[valid]]", "[[invalid]]"):
+            cur = {"filename": None, "tags": []}
+            out[s.strip("[]")].append(cur)
+        elif cur is not None and s.startswith("filename"):
+            cur["filename"] = s.split("=", 1)[1].strip().strip('"')
+        elif cur is not None and s.startswith("tags"):
+            cur["tags"] = [t.strip().strip('"') for t in s.split("=", 1)[1].strip().strip("[]").split(",") if t.strip()]
+    return out
