@@ -1,0 +1,518 @@
+"""needletail_b200 — host-side mirror of needletail's public surface on top of libntgpu's C ABI.
+
+The product is ``libntgpu.so`` (include/ntgpu.h).  This module is the thin Python face of it, with
+the function names of the reference's own Python module (src/python.rs:429-438:
+``parse_fastx_file``, ``parse_fastx_string``, ``normalize_seq``, ``reverse_complement``,
+``decode_phred`` is host-only and omitted) plus batch forms of the ``Sequence`` trait methods
+(src/sequence.rs:156-253) and the fused hot-path call.  There is no CPU fallback: importing works
+anywhere, but every call needs a B200 (``Context()`` raises ``NtgError`` otherwise).
+"""
+import ctypes as C
+import os
+import zlib
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libntgpu.so")
+
+# ntg_status (include/ntgpu.h) — 1..7 == needletail::errors::ParseErrorKind (src/errors.rs:28-43)
+OK = 0
+ERROR_KINDS = {1: "Io", 2: "UnknownFormat", 3: "InvalidStart", 4: "InvalidSeparator", 5: "UnequalLengths",
+               6: "UnexpectedEnd", 7: "EmptyFile", 16: "InvalidArgument", 17: "Cuda", 18: "Nccl", 19: "NoMemory",
+               20: "Unsupported"}
+FORMATS = {0: None, 1: "fasta", 2: "fastq"}
+LINE_ENDINGS = {0: None, 1: "unix", 2: "windows"}
+TALLY_FIELDS = ["n_records", "n_bases", "n_kmers", "n_not_rc", "kmer_sum_lo", "kmer_sum_hi", "n_query",
+                "n_minimizers", "minimizer_sum"]
+
+
+class NtgError(Exception):
+    """Library failure (CUDA, NCCL, bad argument)."""
+
+    def __init__(self, status, msg=""):
+        self.status = status
+        self.kind = ERROR_KINDS.get(status, str(status))
+        super().__init__(f"{self.kind}: {msg}")
+
+
+class NeedletailError(Exception):
+    """Parse error — mirrors needletail.NeedletailError (src/python.rs:53-60, src/errors.rs:46-56)."""
+
+    def __init__(self, kind, line=0, id=None, format=None):
+        self.kind, self.line, self.id, self.format = kind, line, id, format
+        super().__init__(f"{kind} at line {line}" + (f" (record {id!r})" if id else ""))
+
+
+class _Record(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("start", "id_b", "id_e", "seq_b", "seq_e", "qual_b", "qual_e", "all_e",
+                                          "num_bases", "line")]
+
+
+class _ParseError(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("format", C.c_int32), ("line", C.c_uint64), ("record_index", C.c_uint64),
+                ("has_id", C.c_int32), ("id", C.c_char * 236)]
+
+
+class _Records(C.Structure):
+    _fields_ = [("format", C.c_int32), ("line_ending", C.c_int32), ("n_records", C.c_uint64),
+                ("records", C.POINTER(_Record)), ("error", _ParseError), ("final_line", C.c_uint64),
+                ("final_byte", C.c_uint64), ("_priv", C.c_void_p)]
+
+
+class _Items(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("n_items", C.c_uint64), ("item_offs", C.POINTER(C.c_uint64)),
+                ("pos", C.POINTER(C.c_uint32)), ("was_rc", C.POINTER(C.c_uint8)), ("val_lo", C.POINTER(C.c_uint64)),
+                ("val_hi", C.POINTER(C.c_uint64)), ("_priv", C.c_void_p)]
+
+
+class _TallyConfig(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("m", C.c_uint32), ("allow_iupac", C.c_uint32), ("has_query", C.c_uint32),
+                ("query", C.c_uint8 * 64)]
+
+
+class _Tallies(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in TALLY_FIELDS] + [("reserved", C.c_uint64 * 7)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libntgpu.so (built in-tree by needletail_b200/build.py) and declare the ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise NtgError(17, f"{_SO} is missing: run `python needletail_b200/build.py` (nvcc, sm_100a)")
+    L = C.CDLL(_SO)
+    vp, u64, u32, sz, cp = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t, C.c_char_p
+    P = C.POINTER
+    sig = {
+        "ntg_abi_version": ([], C.c_int),
+        "ntg_device_count": ([P(C.c_int)], C.c_int),
+        "ntg_create": ([C.c_int, P(vp)], C.c_int),
+        "ntg_destroy": ([vp], None),
+        "ntg_last_error": ([vp], cp),
+        "ntg_device_info": ([vp, P(C.c_int), P(sz), P(C.c_int), P(C.c_int)], C.c_int),
+        "ntg_sync": ([vp], C.c_int),
+        "ntg_launch_count": ([vp], u64),
+        "ntg_alloc_pinned": ([sz, P(vp)], C.c_int),
+        "ntg_free_pinned": ([vp], C.c_int),
+        "ntg_device_alloc": ([vp, sz, P(u64)], C.c_int),
+        "ntg_device_free": ([vp, u64], C.c_int),
+        "ntg_memcpy_h2d": ([vp, u64, vp, sz], C.c_int),
+        "ntg_memcpy_d2h": ([vp, vp, u64, sz], C.c_int),
+        "ntg_event_record": ([vp, C.c_int], C.c_int),
+        "ntg_event_elapsed_ms": ([vp, C.c_int, C.c_int, P(C.c_float)], C.c_int),
+        "ntg_parse_fastx": ([vp, vp, sz, P(P(_Records))], C.c_int),
+        "ntg_records_free": ([P(_Records)], None),
+        "ntg_normalize": ([vp, vp, vp, sz, C.c_int, vp, vp, vp], C.c_int),
+        "ntg_strip_returns": ([vp, vp, vp, sz, vp, vp, vp], C.c_int),
+        "ntg_reverse_complement": ([vp, vp, vp, sz, vp], C.c_int),
+        "ntg_quality_mask": ([vp, vp, vp, vp, sz, C.c_uint8, vp], C.c_int),
+        "ntg_items_free": ([P(_Items)], None),
+        "ntg_canonical_kmers": ([vp, vp, vp, vp, sz, u32, P(P(_Items))], C.c_int),
+        "ntg_bit_kmers": ([vp, vp, vp, sz, u32, C.c_int, P(P(_Items))], C.c_int),
+        "ntg_bit_minimizers": ([vp, vp, vp, sz, u32, u32, P(P(_Items))], C.c_int),
+        "ntg_bitkmer_reverse_complement": ([vp, vp, sz, u32, vp], C.c_int),
+        "ntg_bitkmer_canonical": ([vp, vp, sz, u32, vp, vp], C.c_int),
+        "ntg_bitkmer_minimizer": ([vp, vp, sz, u32, u32, vp], C.c_int),
+        "ntg_tally_fastx": ([vp, vp, sz, P(_TallyConfig), P(_Tallies), P(_ParseError)], C.c_int),
+        "ntg_tally_fastx_device": ([vp, u64, sz, P(_TallyConfig), P(_Tallies), P(_ParseError)], C.c_int),
+        "ntg_tally_fastx_device_enqueue": ([vp, u64, sz, P(_TallyConfig)], C.c_int),
+        "ntg_tally_fastx_device_collect": ([vp, P(_Tallies), P(_ParseError), P(C.c_float)], C.c_int),
+        "ntg_synth_fastq_device": ([vp, u64, u64, u64, u64, u32, u32], C.c_int),
+        "ntg_synth_fasta_device": ([vp, u64, u64, u64, u64, u32, u32], C.c_int),
+        "ntg_comm_unique_id": ([vp], C.c_int),
+        "ntg_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int),
+        "ntg_comm_allreduce_tallies": ([vp, P(_Tallies)], C.c_int),
+        "ntg_comm_destroy": ([vp], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        f = getattr(L, name)      # raises AttributeError if the .so does not export what the header declares
+        f.argtypes, f.restype = args, res
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def _as_u8(data):
+    if isinstance(data, np.ndarray):
+        assert data.dtype == np.uint8
+        return np.ascontiguousarray(data)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def _batch(seqs):
+    """list of bytes -> (concatenated uint8 array, uint64 offsets)"""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    cat = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8) if seqs else np.zeros(0, dtype=np.uint8)
+    return cat, offs
+
+
+def _ptr(a):
+    return a.ctypes.data if a.size else None
+
+
+class Items:
+    """CSR result of canonical_kmers / bit_kmers / bit_minimizers (one row per emitted item)."""
+
+    def __init__(self, it):
+        n, ni = it.n_seqs, it.n_items
+        self.item_offs = np.ctypeslib.as_array(it.item_offs, shape=(n + 1,)).copy()
+        self.pos = np.ctypeslib.as_array(it.pos, shape=(ni,)).copy() if ni else np.zeros(0, np.uint32)
+        self.was_rc = (np.ctypeslib.as_array(it.was_rc, shape=(ni,)).copy() if ni else np.zeros(0, np.uint8)) if it.was_rc else None
+        self.val_lo = np.ctypeslib.as_array(it.val_lo, shape=(ni,)).copy() if ni else np.zeros(0, np.uint64)
+        self.val_hi = (np.ctypeslib.as_array(it.val_hi, shape=(ni,)).copy() if ni else np.zeros(0, np.uint64)) if it.val_hi else None
+
+    def of(self, i):
+        a, b = int(self.item_offs[i]), int(self.item_offs[i + 1])
+        return slice(a, b)
+
+
+class Context:
+    """One CUDA device + its streams (ntg_ctx).  Not thread-safe, like a `&mut` reader."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.ntg_create(device, C.byref(h))
+        if st != OK:
+            raise NtgError(st, "ntg_create failed (no CUDA device / not sm_100?) — libntgpu has no CPU path")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ntg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != OK:
+            raise NtgError(st, self.lib.ntg_last_error(self.h).decode(errors="replace"))
+
+    # ---- info / memory / timing
+    def device_info(self):
+        sm, mem, ma, mi = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+        self._ck(self.lib.ntg_device_info(self.h, C.byref(sm), C.byref(mem), C.byref(ma), C.byref(mi)))
+        return dict(sm_count=sm.value, total_mem=mem.value, cc=(ma.value, mi.value))
+
+    def launch_count(self):
+        return int(self.lib.ntg_launch_count(self.h))
+
+    def sync(self):
+        self._ck(self.lib.ntg_sync(self.h))
+
+    def device_alloc(self, nbytes):
+        d = C.c_uint64()
+        self._ck(self.lib.ntg_device_alloc(self.h, nbytes, C.byref(d)))
+        return d.value
+
+    def device_free(self, dptr):
+        self._ck(self.lib.ntg_device_free(self.h, dptr))
+
+    def h2d(self, dptr, arr):
+        arr = _as_u8(arr)
+        self._ck(self.lib.ntg_memcpy_h2d(self.h, dptr, arr.ctypes.data, arr.size))
+
+    def d2h(self, dptr, nbytes):
+        out = np.empty(nbytes, dtype=np.uint8)
+        self._ck(self.lib.ntg_memcpy_d2h(self.h, out.ctypes.data, dptr, nbytes))
+        return out
+
+    def event_record(self, slot):
+        self._ck(self.lib.ntg_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self.lib.ntg_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    # ---- (1) record scanner
+    def parse(self, data):
+        """-> Parsed (records before the first error, plus .error) — ntg_parse_fastx"""
+        arr = _as_u8(data)
+        out = C.POINTER(_Records)()
+        self._ck(self.lib.ntg_parse_fastx(self.h, _ptr(arr), arr.size, C.byref(out)))
+        try:
+            return Parsed(arr, out.contents)
+        finally:
+            self.lib.ntg_records_free(out)
+
+    # ---- (2) Sequence trait, batch form
+    def normalize(self, seqs, iupac=False):
+        """list[bytes] -> (list[bytes], changed flags) — sequence::normalize per sequence"""
+        cat, offs = _batch(seqs)
+        out = np.empty(max(1, cat.size), dtype=np.uint8)
+        ooffs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        ch = np.zeros(max(1, len(seqs)), dtype=np.uint8)
+        self._ck(self.lib.ntg_normalize(self.h, _ptr(cat), offs.ctypes.data, len(seqs), int(iupac), out.ctypes.data,
+                                        ooffs.ctypes.data, ch.ctypes.data))
+        return [out[int(ooffs[i]):int(ooffs[i + 1])].tobytes() for i in range(len(seqs))], [bool(x) for x in ch[:len(seqs)]]
+
+    def strip_returns(self, seqs):
+        cat, offs = _batch(seqs)
+        out = np.empty(max(1, cat.size), dtype=np.uint8)
+        ooffs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        ch = np.zeros(max(1, len(seqs)), dtype=np.uint8)
+        self._ck(self.lib.ntg_strip_returns(self.h, _ptr(cat), offs.ctypes.data, len(seqs), out.ctypes.data,
+                                            ooffs.ctypes.data, ch.ctypes.data))
+        return [out[int(ooffs[i]):int(ooffs[i + 1])].tobytes() for i in range(len(seqs))], [bool(x) for x in ch[:len(seqs)]]
+
+    def reverse_complement(self, seqs):
+        cat, offs = _batch(seqs)
+        out = np.empty(max(1, cat.size), dtype=np.uint8)
+        self._ck(self.lib.ntg_reverse_complement(self.h, _ptr(cat), offs.ctypes.data, len(seqs), out.ctypes.data))
+        return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(seqs))]
+
+    def quality_mask(self, seqs, quals, score):
+        cat, offs = _batch(seqs)
+        qcat, _ = _batch(quals)
+        out = np.empty(max(1, cat.size), dtype=np.uint8)
+        self._ck(self.lib.ntg_quality_mask(self.h, _ptr(cat), _ptr(qcat), offs.ctypes.data, len(seqs), score, out.ctypes.data))
+        return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(seqs))]
+
+    def _items(self, fn, *args):
+        out = C.POINTER(_Items)()
+        self._ck(fn(self.h, *args, C.byref(out)))
+        try:
+            return Items(out.contents)
+        finally:
+            self.lib.ntg_items_free(out)
+
+    def canonical_kmers(self, seqs, k, rcs=None):
+        cat, offs = _batch(seqs)
+        rc = _batch(rcs)[0] if rcs is not None else None
+        return self._items(self.lib.ntg_canonical_kmers, _ptr(cat), _ptr(rc) if rc is not None else None,
+                           offs.ctypes.data, len(seqs), k)
+
+    def bit_kmers(self, seqs, k, canonical=False):
+        cat, offs = _batch(seqs)
+        return self._items(self.lib.ntg_bit_kmers, _ptr(cat), offs.ctypes.data, len(seqs), k, int(canonical))
+
+    def bit_minimizers(self, seqs, k, m):
+        cat, offs = _batch(seqs)
+        return self._items(self.lib.ntg_bit_minimizers, _ptr(cat), offs.ctypes.data, len(seqs), k, m)
+
+    def bitkmer_reverse_complement(self, vals, k):
+        v = np.ascontiguousarray(vals, dtype=np.uint64); out = np.empty_like(v)
+        self._ck(self.lib.ntg_bitkmer_reverse_complement(self.h, _ptr(v), v.size, k, out.ctypes.data))
+        return out
+
+    def bitkmer_canonical(self, vals, k):
+        v = np.ascontiguousarray(vals, dtype=np.uint64); out = np.empty_like(v); fl = np.zeros(max(1, v.size), np.uint8)
+        self._ck(self.lib.ntg_bitkmer_canonical(self.h, _ptr(v), v.size, k, out.ctypes.data, fl.ctypes.data))
+        return out, fl[:v.size]
+
+    def bitkmer_minimizer(self, vals, k, m):
+        v = np.ascontiguousarray(vals, dtype=np.uint64); out = np.empty_like(v)
+        self._ck(self.lib.ntg_bitkmer_minimizer(self.h, _ptr(v), v.size, k, m, out.ctypes.data))
+        return out
+
+    # ---- (3) fused hot path
+    @staticmethod
+    def _cfg(k, m, iupac, query):
+        cfg = _TallyConfig(k=k, m=m, allow_iupac=int(iupac), has_query=int(query is not None))
+        if query is not None:
+            q = bytes(query)
+            for i, b in enumerate(q[:64]):
+                cfg.query[i] = b
+        return cfg
+
+    @staticmethod
+    def _tally_result(t, e):
+        d = {f: int(getattr(t, f)) for f in TALLY_FIELDS}
+        d["err_kind"] = ERROR_KINDS.get(e.kind) if e.kind else None
+        d["err_line"] = int(e.line)
+        return d
+
+    def tally(self, data, k, m=0, iupac=False, query=None):
+        """Host bytes -> tallies dict (the end-to-end call: H2D inside) — ntg_tally_fastx"""
+        arr = _as_u8(data)
+        cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
+        self._ck(self.lib.ntg_tally_fastx(self.h, _ptr(arr), arr.size, C.byref(cfg), C.byref(t), C.byref(e)))
+        return self._tally_result(t, e)
+
+    def tally_ptr(self, host_ptr, nbytes, k, m=0, iupac=False, query=None):
+        cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
+        self._ck(self.lib.ntg_tally_fastx(self.h, host_ptr, nbytes, C.byref(cfg), C.byref(t), C.byref(e)))
+        return self._tally_result(t, e)
+
+    def tally_device(self, dptr, nbytes, k, m=0, iupac=False, query=None):
+        cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
+        self._ck(self.lib.ntg_tally_fastx_device(self.h, dptr, nbytes, C.byref(cfg), C.byref(t), C.byref(e)))
+        return self._tally_result(t, e)
+
+    def tally_device_enqueue(self, dptr, nbytes, k, m=0, iupac=False, query=None):
+        cfg = self._cfg(k, m, iupac, query)
+        self._ck(self.lib.ntg_tally_fastx_device_enqueue(self.h, dptr, nbytes, C.byref(cfg)))
+
+    def tally_device_collect(self):
+        t = _Tallies(); e = _ParseError(); ms = C.c_float()
+        self._ck(self.lib.ntg_tally_fastx_device_collect(self.h, C.byref(t), C.byref(e), C.byref(ms)))
+        d = self._tally_result(t, e)
+        d["fused_kernel_ms"] = ms.value
+        return d
+
+    # ---- (4) synthetic inputs
+    def synth_fastq_device(self, dptr, seed, rec0, nrec, read_len, n_thresh=0):
+        self._ck(self.lib.ntg_synth_fastq_device(self.h, dptr, seed, rec0, nrec, read_len, n_thresh))
+
+    def synth_fasta_device(self, dptr, seed, rec0, nrec, read_len, n_thresh=0):
+        self._ck(self.lib.ntg_synth_fasta_device(self.h, dptr, seed, rec0, nrec, read_len, n_thresh))
+
+    # ---- (5) multi-GPU
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        st = self.lib.ntg_comm_unique_id(buf)
+        if st != OK:
+            raise NtgError(st, "ncclGetUniqueId")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, uid):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.ntg_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_allreduce_tallies(self, d):
+        t = _Tallies()
+        for f in TALLY_FIELDS:
+            setattr(t, f, d[f])
+        self._ck(self.lib.ntg_comm_allreduce_tallies(self.h, C.byref(t)))
+        return {f: int(getattr(t, f)) for f in TALLY_FIELDS}
+
+
+class Record:
+    """Mirrors needletail's Python Record (src/python.rs:125-264): id, seq, qual as str."""
+
+    __slots__ = ("id", "seq", "qual", "raw_seq", "all", "num_bases", "line", "byte")
+
+    def __init__(self, data, r, fmt):
+        b = data
+        self.id = b[r.id_b:r.id_e].tobytes().decode("utf-8", errors="replace")
+        self.raw_seq = b[r.seq_b:r.seq_e].tobytes()
+        # Record.seq is SequenceRecord::seq(): raw_seq minus all \r\n (src/parser/record.rs:84-89, python.rs:136-142)
+        self.seq = self.raw_seq.replace(b"\n", b"").replace(b"\r", b"").decode("utf-8", errors="replace")
+        self.qual = b[r.qual_b:r.qual_e].tobytes().decode("utf-8", errors="replace") if fmt == "fastq" else None
+        self.all = b[r.start:r.all_e].tobytes()
+        self.num_bases = int(r.num_bases)
+        self.line = int(r.line)
+        self.byte = int(r.start)
+
+    def is_fasta(self):
+        return self.qual is None
+
+    def is_fastq(self):
+        return self.qual is not None
+
+
+class Parsed:
+    def __init__(self, data, rs):
+        self.format = FORMATS[rs.format]
+        self.line_ending = LINE_ENDINGS[rs.line_ending]
+        self.final_line, self.final_byte = int(rs.final_line), int(rs.final_byte)
+        n = int(rs.n_records)
+        self.table = np.ctypeslib.as_array(C.cast(rs.records, C.POINTER(C.c_uint64)), shape=(n, 10)).copy() if n else np.zeros((0, 10), np.uint64)
+        self.records = [Record(data, rs.records[i], self.format) for i in range(n)]
+        e = rs.error
+        self.err_kind = ERROR_KINDS.get(e.kind) if e.kind else None
+        self.err_line = int(e.line)
+        self.err_record_index = int(e.record_index)
+        self.err_id = e.id if e.has_id else None
+
+    def error(self):
+        return NeedletailError(self.err_kind, self.err_line, self.err_id, self.format) if self.err_kind else None
+
+
+# ------------------------------------------------------------------------------------------------
+# module-level API with the reference's Python names (src/python.rs:291-427)
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+def _decompress(raw):
+    """Host side of the boundary: compression sniff (src/parser/mod.rs:27-35,95-147).  gzip is
+    multi-member like flate2::MultiGzDecoder; bz2/xz via the stdlib; zstd is not available here."""
+    if len(raw) >= 2:
+        magic = raw[:2]
+        if magic == b"\x1f\x8b":
+            out, d = [], raw
+            while d:
+                z = zlib.decompressobj(16 + zlib.MAX_WBITS)
+                out.append(z.decompress(d)); out.append(z.flush())
+                d = z.unused_data
+            return b"".join(out)
+        if magic == b"BZ":
+            import bz2
+            return bz2.decompress(raw)
+        if magic == b"\xfd7":
+            import lzma
+            return lzma.decompress(raw)
+        if magic == b"\x28\xb5":
+            raise NtgError(20, "zstd input: no decoder in this environment")
+    return raw
+
+
+class FastxReader:
+    """Iterator over records (python.rs:62-86); raises NeedletailError at the first invalid record,
+    after yielding the valid ones before it — the reference's iteration order."""
+
+    def __init__(self, data, ctx=None):
+        ctx = ctx or default_context()
+        raw = _decompress(bytes(data))
+        if len(data) >= 2 and len(raw) < 1 and raw != data:
+            raise NeedletailError("EmptyFile")
+        self._p = ctx.parse(raw)
+        if self._p.err_kind in ("EmptyFile", "UnknownFormat") and not self._p.records:
+            raise self._p.error()          # parse_fastx_reader fails up front (mod.rs:88-91,44)
+        self._i = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._i < len(self._p.records):
+            r = self._p.records[self._i]
+            self._i += 1
+            return r
+        if self._p.err_kind and self._i == len(self._p.records):
+            self._i += 1
+            raise self._p.error()
+        raise StopIteration
+
+
+def parse_fastx_file(path, ctx=None):
+    try:
+        with open(os.fspath(path), "rb") as f:
+            data = f.read()
+    except OSError as e:
+        raise NeedletailError("Io") from e
+    return FastxReader(data, ctx)
+
+
+def parse_fastx_string(content, ctx=None):
+    return FastxReader(content.encode() if isinstance(content, str) else content, ctx)
+
+
+def normalize_seq(seq, iupac=False, ctx=None):
+    out, _ = (ctx or default_context()).normalize([seq.encode() if isinstance(seq, str) else seq], iupac)
+    return out[0].decode()
+
+
+def reverse_complement(seq, ctx=None):
+    out = (ctx or default_context()).reverse_complement([seq.encode() if isinstance(seq, str) else seq])
+    return out[0].decode()

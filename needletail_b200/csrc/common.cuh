@@ -1,0 +1,121 @@
+// common.cuh — shared host/device helpers for libntgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ntgpu.h"
+
+// ----------------------------------------------------------------------------- context
+struct ntg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;        // compute stream: every kernel is launched here
+    cudaStream_t copy_stream = nullptr;   // H2D feed for the end-to-end path
+    cudaEvent_t events[64] = {};
+    std::string last_error;
+    uint64_t launches = 0;
+    // fused path state (fused.cu)
+    struct FusedState* fused = nullptr;
+    // NCCL (nccl_dyn.cpp)
+    void* nccl_comm = nullptr;
+    void* nccl_buf = nullptr;             // device staging for the tallies all-reduce
+};
+
+int ntg_set_error(ntg_ctx* ctx, int status, const char* fmt, ...);
+
+#define NTG_CUDA(ctx, expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return ntg_set_error((ctx), NTG_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,  \
+                                 cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define NTG_TRY(expr)                  \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != NTG_OK) return _s;   \
+    } while (0)
+
+// RAII device buffer (freed on scope exit; allocation failures surface as NTG_ENOMEM)
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    }
+};
+// RAII pinned host buffer
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMallocHost((void**)&p, (count ? count : 1) * sizeof(T));
+    }
+    T* release() { T* q = p; p = nullptr; return q; }
+};
+
+// ----------------------------------------------------------------------------- byte classes
+// Built once on the host (luts.cuh) and copied to device memory at ntg_create.
+//  c_norm[iupac][b] : output byte of sequence::normalize (src/sequence.rs:19-62); 0 = deleted
+//  c_comp[b]        : sequence::complement (src/sequence.rs:67-105)
+//  c_code[b]        : 0..3 = A/C/G/T (case-insensitive, src/bitkmer.rs:5-18 == kmer.rs:6-8 good set), 4 = not a good base
+//  c_ncls[b]        : class of b *after* normalize: 0..3 = ACGT, 4 = kept but not ACGT (N, -, IUPAC), 5 = deleted
+// (global memory + __ldg: per-lane divergent indices would serialise in __constant__ memory)
+// libntgpu is a unity build (ntgpu.cu includes every *.cuh once), hence `static`.
+static __device__ uint8_t c_norm[2][256];
+static __device__ uint8_t c_comp[256];
+static __device__ uint8_t c_code[256];
+static __device__ uint8_t c_ncls[256];
+static int ntg_upload_luts(ntg_ctx* ctx);
+
+// ----------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+// 2 * k-bit mask with k <= 32 (k == 32 -> all ones), mirrors Rust's wrapping pow in bitkmer.rs:31
+__host__ __device__ __forceinline__ uint64_t mask2k(uint32_t k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull); }
+
+// bitkmer::reverse_complement (src/bitkmer.rs:112-132) via brev + adjacent-bit swap
+__device__ __forceinline__ uint64_t bit_rc(uint64_t x, uint32_t k) {
+    uint64_t r = __brevll(x);                                               // reverses single bits
+    r = ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);  // restore order inside each 2-bit group
+    r = ~r;
+    uint32_t sh = 2 * (32 - k);
+    return sh >= 64 ? 0ull : (r >> sh);
+}
+// bitkmer::minimizer (src/bitkmer.rs:146-162), RC at width k
+__device__ __forceinline__ uint64_t bit_minimizer_slow(uint64_t kmer, uint32_t k, uint32_t m) {
+    uint64_t lowest = ~0ull, bm = mask2k(m);
+    for (uint32_t i = 0; i + m <= k; i++) {
+        uint64_t cur = kmer & bm;
+        if (cur < lowest) lowest = cur;
+        uint64_t r = bit_rc(cur, k);
+        if (r < lowest) lowest = r;
+        kmer >>= 2;
+    }
+    return lowest;
+}
+
+// ----------------------------------------------------------------------------- device-wide scan
+// exclusive prefix sum of n uint8 flags into uint32 (out has n+1 entries; out[n] = total).
+// tmp must hold scan_tmp_count(n) uint32.  Three kernels (reduce / scan partials / downsweep).
+static size_t scan_tmp_count(size_t n);
+static int exclusive_scan_u8(ntg_ctx* ctx, const uint8_t* flags, uint32_t* out, size_t n, uint32_t* tmp);

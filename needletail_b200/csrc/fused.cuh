@@ -1,0 +1,624 @@
+// fused.cuh — the hot path: ONE pass over FASTX bytes -> tallies.
+//
+//   delimiter scan (fastq.rs:155-187,306-308 / fasta.rs:220-243)  +  validate (fastq.rs:240-285)
+//   + normalize (sequence.rs:19-62) + reverse_complement (sequence.rs:67-105,202-208)
+//   + CanonicalKmers (kmer.rs:84-129) + BitNuclKmer/minimizer (bitkmer.rs:26-162)
+//
+// Persistent CTAs claim 56 KiB tiles in order (atomic ticket).  Per tile:
+//   P0  the tile (+128 B back halo) is brought into shared memory by one cp.async.bulk (TMA 1-D
+//       bulk copy, SASS UBLKCP) completing on an mbarrier;
+//   P1  every thread scans one 256 B row for '\n' with 32-bit SIMD-in-register tests (rotated
+//       word order => bank-conflict free);
+//   P2  block scan -> sorted newline list; the tile's aggregate (newline count, last four newline
+//       positions, FASTA header state) is published and the global prefix is obtained by
+//       decoupled look-back (single pass: the input is read from HBM exactly once);
+//   P3  line roles (FASTQ: newline ordinal mod 4; FASTA: '>' at line start) -> validation events,
+//       n_records / n_bases, and one sequential "walker" per sequence-line fragment: 2-bit rolling
+//       forward / reverse-complement words, canonical select, sliding-window (van Herk) minimizer;
+//   P4  per-thread tallies stay in registers across tiles; one block reduction + 9 atomics per CTA.
+// Anything the fast path cannot prove clean (parse error, > NLMAX newlines in a tile, whitespace
+// runs longer than the halo) raises a flag and the host re-runs the exact materialising path.
+// Part of the unity build (ntgpu.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fused {
+constexpr int NT = 224;                  // 7 warps; 3 CTAs per SM
+constexpr int ROWB = 256;                // bytes scanned per thread in P1
+constexpr int ROWW = ROWB / 4;
+constexpr int TILE = NT * ROWB;          // 57344
+constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
+constexpr int NLMAX = 3072;              // newline capacity per tile (mean line >= 18.7 B)
+constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
+constexpr int LONGMAX = TILE / SEG + 2;
+constexpr uint64_t NONE = ~0ull;
+constexpr uint64_t INHDR = ~0ull - 1;
+
+enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4 };
+
+// carried scan state (prefix over tiles)
+struct SState {
+    uint64_t count;        // newlines so far
+    uint64_t last[4];      // global positions of the most recent newlines, last[0] newest; NONE if absent
+    uint64_t n_starts;     // FASTA record starts
+    uint64_t hdr;          // FASTA: NONE = no record start in this span; INHDR = span ends inside a header
+                           //        line; else position of the newline that ended the latest header
+    uint64_t first_nl;     // FASTA: first newline of the span (NONE if none)
+};
+struct __align__(128) TileSlot {
+    SState agg;
+    SState inc;
+    uint32_t flag;         // 0 = empty, 1 = aggregate published, 2 = inclusive prefix published
+    uint32_t pad[15];
+};
+
+__host__ __device__ inline SState identity_state() {
+    SState s; s.count = 0; s.n_starts = 0; s.hdr = NONE; s.first_nl = NONE;
+    for (int i = 0; i < 4; i++) s.last[i] = NONE;
+    return s;
+}
+// a = earlier span, b = later span
+__host__ __device__ inline SState combine(const SState& a, const SState& b) {
+    SState r;
+    r.count = a.count + b.count;
+    int j = 0;
+    for (int i = 0; i < 4 && j < 4; i++) if (b.last[i] != NONE) r.last[j++] = b.last[i];
+    for (int i = 0; i < 4 && j < 4; i++) if (a.last[i] != NONE) r.last[j++] = a.last[i];
+    for (; j < 4; j++) r.last[j] = NONE;
+    r.n_starts = a.n_starts + b.n_starts;
+    r.first_nl = a.first_nl != NONE ? a.first_nl : b.first_nl;
+    if (b.hdr != NONE) r.hdr = b.hdr;
+    else if (a.hdr == INHDR) r.hdr = (b.first_nl != NONE) ? b.first_nl : INHDR;
+    else r.hdr = a.hdr;
+    return r;
+}
+
+struct Params {
+    const uint8_t* bytes;
+    uint64_t n;
+    uint64_t num_tiles;
+    TileSlot* slots;
+    uint32_t* ticket;
+    unsigned long long* tallies;      // 16 x u64
+    uint32_t* flags;
+    SState* final_state;
+    uint32_t k, m, w;
+    int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
+    int has_query;
+    uint64_t q_lo, q_hi;
+};
+
+struct Acc {
+    uint64_t n_records = 0, n_bases = 0, n_kmers = 0, n_not_rc = 0, ksum_lo = 0, ksum_hi = 0, n_query = 0, n_mini = 0, msum = 0;
+};
+
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- shared memory layout ------------------------------------------------------------------
+struct __align__(16) Smem {
+    uint8_t halo[HALO];
+    uint8_t tile[TILE];
+    uint16_t nl[NLMAX + 8];            // sorted tile-relative newline offsets
+    uint16_t rstart[NLMAX + 8];        // FASTA: per line, tile-relative (+HALO) start of its sequence region
+    uint8_t lut[256];                  // c_ncls (+ CR/LF split: 6)
+    uint64_t bar;
+    uint32_t warp_tmp[NT / 32 + 2];
+    uint64_t red[NT / 32][9];
+    SState prefix;                     // exclusive prefix of this tile
+    uint32_t tile_idx;
+    uint32_t n_long;
+    uint32_t long_line[LONGMAX];       // line indices of long sequence lines
+    uint32_t long_pref[LONGMAX + 1];   // exclusive prefix of piece counts
+    int32_t bcast[4];
+};
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* tmp) {
+    constexpr int NW = NT / 32;
+    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) tmp[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NW; i++) { uint32_t t = tmp[i]; tmp[i] = s; s += t; } tmp[NW] = s; }
+    __syncthreads();
+    uint32_t r = inc - v + tmp[w];
+    *total = tmp[NW];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ uint32_t block_incl_max(uint32_t v, uint32_t* tmp) {   // inclusive max-scan across threads
+    constexpr int NW = NT / 32;
+    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, t); }
+    if (lane == 31) tmp[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NW; i++) { uint32_t t = tmp[i]; tmp[i] = s; s = max(s, t); } }
+    __syncthreads();
+    uint32_t r = max(inc, tmp[w]);
+    __syncthreads();
+    return r;
+}
+
+// =============================================================================== the walker
+// Processes the sequence bytes sb[a..b) (tile-relative; sb[-HALO..-1] is the back halo) of one
+// sequence-line fragment.  `lo` = lowest index the warm-up may read; lo_exact tells whether lo is the
+// true start of the sequence region (nothing before it belongs to this sequence).
+// K-mers are owned by their LAST base: every k-mer whose last base lies in [a,b) is tallied here.
+//   KW   : 1 -> k <= 32 (u64 words), 2 -> k <= 64 (2 x u64)
+//   MINI : also bit_kmers(k,false) -> bitkmer::minimizer(m)      (KW == 1 only)
+//   W    : compile-time window k-m+1 (0 = run-time window, arrays indexed dynamically)
+template <int KW, bool MINI, int W>
+__device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int a, int b, int lo,
+                                     bool lo_exact, const Params& P, Acc& acc, bool count_bases, uint32_t& slow) {
+    const int k = (int)P.k;
+    // ---- warm-up: step back over at most k-1 kept good bases
+    int ws = a;
+    {
+        int got = 0, p = a - 1;
+        bool stopped = false;
+        while (p >= lo && got < k - 1) {
+            uint8_t c = lut[sb[p]];
+            if (c <= 3) { got++; ws = p; }
+            else if (c == 4) { stopped = true; break; }     // a non-ACGT base resets everything before it
+            p--;
+        }
+        if (!stopped && got < k - 1 && p < lo && !lo_exact) slow |= FLAG_HALO_OVERFLOW;
+    }
+    uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;              // forward / reverse-complement words (x1 = high word, KW == 2)
+    int run = 0;
+    const uint64_t kmask = (KW == 1) ? mask2k(P.k) : mask2k(P.k - 32);        // mask of the top word
+    const int rshift = (KW == 1) ? 2 * (k - 1) : 2 * (k - 33);               // where a new rc base enters the top word
+    // minimizer: sliding-window minimum by van Herk block decomposition over the stream of kept bases
+    const uint64_t mmask = MINI ? mask2k(P.m) : 0, lmask = MINI ? mask2k(P.k - P.m) : 0;
+    constexpr int WA = MINI ? ((W > 0) ? W : 32) : 1;
+    uint64_t cur[WA + 1], suf[WA + 1], pre = 0;
+#pragma unroll
+    for (int i = 0; i <= WA; i++) { cur[i] = 0; suf[i] = 0; }
+    const int w = MINI ? ((W > 0) ? W : (int)P.w) : 1;
+
+    int p = ws;
+    for (;;) {
+#pragma unroll
+        for (int i = 0; i < ((W > 0) ? W : w); i++) {
+            uint8_t c;
+            do {                                             // fetch the next kept base
+                if (p >= b) return;
+                c = lut[sb[p]];
+                if (count_bases && p >= a && c != 6) acc.n_bases++;   // FASTA num_bases: everything but \r \n
+                p++;
+            } while (c >= 5);
+            const uint64_t code = c & 3;
+            run = (c <= 3) ? run + 1 : 0;                    // a bad base (c == 4) still occupies a slot
+            if (KW == 1) {
+                f0 = ((f0 << 2) | code) & kmask;
+                r0 = (r0 >> 2) | ((3 - code) << rshift);
+            } else {
+                f1 = ((f1 << 2) | (f0 >> 62)) & kmask;
+                f0 = (f0 << 2) | code;
+                r0 = (r0 >> 2) | (r1 << 62);
+                r1 = (r1 >> 2) | ((3 - code) << rshift);
+            }
+            uint64_t win = 0;
+            if (MINI) {
+                // score of the m-mer ending here: min(x, RC_k(x)), x = f & mmask, RC_k(x) = r | lmask  (bitkmer.rs:146-162)
+                const uint64_t x = f0 & mmask, y = r0 | lmask;
+                const uint64_t s = x < y ? x : y;
+                pre = (i == 0) ? s : (s < pre ? s : pre);
+                cur[i] = s;
+                const uint64_t sv = suf[i + 1];
+                win = (i == w - 1) ? pre : (sv < pre ? sv : pre);
+            }
+            if (p > a && run >= k) {                         // last base index p-1 >= a
+                const bool lt = (KW == 1) ? (f0 < r0) : (f1 < r1 || (f1 == r1 && f0 < r0));
+                acc.n_kmers++;
+                acc.n_not_rc += lt ? 1 : 0;                  // ties => was_rc = true (kmer.rs:124-128)
+                const uint64_t c0 = lt ? f0 : r0, c1 = lt ? f1 : r1;
+                acc.ksum_lo += c0;
+                if (KW == 2) acc.ksum_hi += c1;
+                if (P.has_query && c0 == P.q_lo && (KW == 1 || c1 == P.q_hi)) acc.n_query++;
+                if (MINI) { acc.n_mini++; acc.msum += win; }
+            }
+        }
+        if (MINI) {                                          // suffix minima of the block just finished
+            suf[w - 1] = cur[w - 1];
+#pragma unroll
+            for (int j = WA - 2; j >= 0; j--) if (j < w - 1) { const uint64_t t = suf[j + 1]; suf[j] = cur[j] < t ? cur[j] : t; }
+        }
+    }
+}
+
+// =============================================================================== the kernel
+__device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
+    // global position -> byte, from shared memory when resident, else from global memory
+    if (gpos + halo >= tile_start && gpos < tile_start + TILE) return sb[(int64_t)gpos - (int64_t)tile_start];
+    return gpos < P.n ? P.bytes[gpos] : 0;
+}
+
+template <int KW, bool MINI, int W>
+__global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
+                                                 const uint32_t epoch, uint32_t* __restrict__ ticket) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31;
+    for (int i = tid; i < 256; i += NT) {
+        uint8_t c = c_ncls[i];
+        if (i == '\r' || i == '\n') c = 6;
+        S.lut[i] = c;
+    }
+    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0, slow = 0;
+    Acc acc;
+    const uint8_t* sb = S.tile;
+    const bool fasta = P.format == NTG_FMT_FASTA;
+
+    for (;;) {
+        if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint64_t t = tile_begin + S.tile_idx;
+        if (t >= tile_end) break;
+        const uint64_t tile_start = t * (uint64_t)TILE;
+        const uint32_t avail = (uint32_t)min((uint64_t)TILE, P.n - tile_start);
+        const uint32_t halo = t > 0 ? HALO : 0;
+        const uint32_t bulk = avail & ~15u;
+
+        // ---- P0: stage the tile (+ back halo) with one bulk async copy
+        if (tid == 0 && halo + bulk) {
+            mbar_expect_tx(&S.bar, halo + bulk);
+            bulk_g2s(S.halo + (HALO - halo), P.bytes + tile_start - halo, halo + bulk, &S.bar);
+        }
+        if (avail < TILE) for (uint32_t i = bulk + tid; i < TILE; i += NT) S.tile[i] = i < avail ? P.bytes[tile_start + i] : 0;
+        if (t == 0) for (int i = tid; i < HALO; i += NT) S.halo[i] = 0;
+        if (halo + bulk) { mbar_wait(&S.bar, parity); parity ^= 1; }
+        __syncthreads();
+
+        // ---- P1: newline scan of this thread's 256 B row (rotated word order: conflict-free LDS.32)
+        uint32_t cnt = 0;
+        uint64_t wmask = 0;
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + tid * ROWW;
+#pragma unroll 8
+        for (int j = 0; j < ROWW; j++) {
+            const uint32_t jj = (j + lane) & (ROWW - 1);
+            const uint32_t x = row[jj] ^ 0x0A0A0A0Au;
+            if ((x - 0x01010101u) & ~x & 0x80808080u) {             // exact as a boolean: some byte is '\n'
+                wmask |= 1ull << jj;
+                uint32_t z = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                z = ~(z | x | 0x7F7F7F7Fu);                          // 0x80 in every byte that is exactly '\n'
+                cnt += __popc(z);
+            }
+        }
+        // ---- P2: ordered newline list
+        uint32_t C;
+        const uint32_t off = block_excl_scan(cnt, &C, S.warp_tmp);
+        const bool overflow = C > NLMAX;
+        if (overflow) slow |= FLAG_NL_OVERFLOW;
+        if (!overflow && cnt) {
+            uint32_t o = off;
+            uint64_t mk = wmask;
+            while (mk) {
+                const int jj = __ffsll((long long)mk) - 1;
+                mk &= mk - 1;
+                const uint32_t wv = row[jj];
+#pragma unroll
+                for (int bsel = 0; bsel < 4; bsel++)
+                    if (((wv >> (8 * bsel)) & 0xFF) == '\n') S.nl[o++] = (uint16_t)(tid * ROWB + jj * 4 + bsel);
+            }
+        }
+        __syncthreads();
+        const uint32_t Cs = overflow ? 0 : C;                          // lines are only interpreted when the list is complete
+        // line i (0..Cs) spans (nl[i-1], nl[i]) ; helpers on tile-relative coordinates
+        auto line_start_rel = [&](uint32_t i) -> int { return i ? (int)S.nl[i - 1] + 1 : 0; };   // for i == 0: start of the in-tile fragment
+        const bool line0_starts_here = (t == 0) || (sb[-1] == '\n');
+
+        // ---- P2b: FASTA start events that do not need the prefix
+        uint32_t my_last_start = 0, my_nstarts = 0;                    // (line index + 1) of the last start seen by this thread
+        if (fasta) {
+            for (uint32_t i = tid; i <= Cs; i += NT) {
+                const int s = line_start_rel(i);
+                const bool starts = (i > 0 || line0_starts_here) && (uint32_t)s < avail;
+                if (starts && sb[s] == '>') { my_last_start = i + 1; my_nstarts++; }
+            }
+        }
+        uint32_t last_start1 = 0, nstarts_tot = 0;
+        if (fasta) {
+            last_start1 = block_incl_max(my_last_start, S.warp_tmp);
+            // broadcast the block-wide max / sum through the last thread
+            uint32_t tot; block_excl_scan(my_nstarts, &tot, S.warp_tmp); nstarts_tot = tot;
+            if (tid == NT - 1) S.bcast[0] = (int32_t)last_start1;
+            __syncthreads();
+            last_start1 = (uint32_t)S.bcast[0];
+        }
+
+        // ---- P2c: publish aggregate, decoupled look-back, publish inclusive prefix (thread 0)
+        if (tid == 0) {
+            SState agg = identity_state();
+            agg.count = C;
+            if (!overflow) for (uint32_t j = 0; j < 4 && j < C; j++) agg.last[j] = tile_start + S.nl[C - 1 - j];
+            if (fasta) {
+                agg.n_starts = nstarts_tot;
+                agg.first_nl = Cs ? tile_start + S.nl[0] : NONE;
+                if (last_start1) { const uint32_t L = last_start1 - 1; agg.hdr = (L < Cs) ? tile_start + S.nl[L] : INHDR; }
+            }
+            TileSlot* slot = &P.slots[t];
+            SState pre = identity_state();
+            if (t > 0) {
+                slot->agg = agg;
+                __threadfence();
+                st_release_u32(&slot->flag, epoch * 4 + 1);
+                SState accst = identity_state();
+                uint64_t j = t - 1;
+                for (;;) {
+                    const uint32_t f = ld_acquire_u32(&P.slots[j].flag);
+                    if ((f >> 2) != epoch || (f & 3) == 0) { __nanosleep(32); continue; }
+                    if ((f & 3) == 2) { pre = combine(P.slots[j].inc, accst); break; }
+                    accst = combine(P.slots[j].agg, accst);
+                    j--;                                                // tile 0 always publishes state 2
+                }
+            }
+            const SState inc = combine(pre, agg);
+            slot->inc = inc;
+            __threadfence();
+            st_release_u32(&slot->flag, epoch * 4 + 2);
+            S.prefix = pre;
+            if (t + 1 == P.num_tiles) *P.final_state = inc;
+        }
+        __syncthreads();
+        const SState pre = S.prefix;
+        // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
+        auto prev_nl = [&](uint32_t i, uint32_t back) -> uint64_t {
+            if (i >= back) return tile_start + S.nl[i - back];
+            const uint32_t r = back - i - 1;
+            return r < 4 ? pre.last[r] : NONE;
+        };
+        auto cr_before = [&](uint64_t q, uint64_t prevq) -> uint32_t {      // trim_cr on the line (prevq, q)
+            const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
+            return (q > ls && byte_at(P, sb, tile_start, halo, q - 1) == '\r') ? 1u : 0u;
+        };
+
+        S.n_long = 0;
+        __syncthreads();
+        if (!fasta) {
+            // ---------------------------------------------------------------------------- FASTQ
+            const uint32_t ord0 = (uint32_t)(pre.count & 3);
+            for (uint32_t i = tid; i <= Cs; i += NT) {
+                const uint32_t role = (ord0 + i) & 3;                     // 0 header, 1 sequence, 2 separator, 3 quality
+                const int s = line_start_rel(i);
+                const bool starts = (i > 0 || line0_starts_here) && (uint32_t)s < avail;
+                if (starts) {                                             // validate(): fastq.rs:240-263
+                    if (role == 0 && sb[s] != '@') slow |= FLAG_PARSE_ERROR;
+                    if (role == 2 && sb[s] != '+') slow |= FLAG_PARSE_ERROR;
+                }
+                if (i < Cs) {                                             // the line ends in this tile at newline q
+                    const uint64_t q = tile_start + S.nl[i];
+                    if (role == 1) {
+                        const uint64_t p1 = prev_nl(i, 1);
+                        const uint64_t ls = p1 == NONE ? 0 : p1 + 1;
+                        acc.n_bases += (q - ls) - cr_before(q, p1);
+                    } else if (role == 3) {
+                        const uint64_t q2 = prev_nl(i, 1), q1 = prev_nl(i, 2), q0 = prev_nl(i, 3);
+                        if (q2 == NONE || q1 == NONE || q0 == NONE) slow |= FLAG_PARSE_ERROR;   // inconsistent state
+                        else {
+                            const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
+                            const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
+                            if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;                   // fastq.rs:276-284
+                            acc.n_records++;
+                        }
+                    }
+                }
+                if (role == 1) {                                          // sequence-line fragment inside the tile
+                    const int a = s, b = (i < Cs) ? (int)S.nl[i] : (int)avail;
+                    if (b > a) {
+                        int lo; bool lo_exact;
+                        if (i > 0 || line0_starts_here) { lo = a; lo_exact = true; }
+                        else {
+                            const uint64_t p1 = pre.last[0];
+                            const int64_t ls = (p1 == NONE ? 0 : (int64_t)p1 + 1) - (int64_t)tile_start;
+                            lo_exact = ls >= -(int64_t)halo;
+                            lo = lo_exact ? (int)ls : -(int)halo;
+                        }
+                        if (b - a <= SEG) walk<KW, MINI, W>(sb, S.lut, a, b, lo, lo_exact, P, acc, false, slow);
+                        else { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; }
+                    }
+                }
+            }
+        } else {
+            // ---------------------------------------------------------------------------- FASTA
+            const bool line0_hdr_cont = !line0_starts_here && pre.hdr == INHDR;
+            auto is_header = [&](uint32_t i) -> bool {
+                if (i == 0 && !line0_starts_here) return line0_hdr_cont;
+                const int s = line_start_rel(i);
+                return (uint32_t)s < avail && sb[s] == '>';
+            };
+            // exclusive max-scan over lines of (end of header line + 1 + HALO): start of the sequence region
+            const uint32_t per = (Cs + 1 + NT - 1) / NT;
+            const uint32_t i0 = min(tid * per, Cs + 1), i1 = min(i0 + per, Cs + 1);
+            uint32_t lm = 0;
+            for (uint32_t i = i0; i < i1; i++) if (i < Cs && is_header(i)) lm = max(lm, (uint32_t)S.nl[i] + 1 + HALO);
+            const uint32_t incl = block_incl_max(lm, S.warp_tmp);
+            uint32_t run = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) run = 0;
+            // exclusive value for this thread = inclusive value of the previous thread
+            __shared__ uint32_t s_prev[NT / 32 + 1];
+            if (lane == 31) s_prev[tid >> 5] = incl;
+            __syncthreads();
+            if (lane == 0 && tid > 0) run = s_prev[(tid >> 5) - 1];
+            for (uint32_t i = i0; i < i1; i++) {
+                S.rstart[i] = (uint16_t)run;
+                if (i < Cs && is_header(i)) run = max(run, (uint32_t)S.nl[i] + 1 + HALO);
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i <= Cs; i += NT) {
+                if (is_header(i)) continue;
+                const int a = line_start_rel(i), b = (i < Cs) ? (int)S.nl[i] : (int)avail;
+                if (b <= a) continue;
+                int lo; bool lo_exact;
+                const uint32_t rs = S.rstart[i];
+                if (rs) { lo = (int)rs - HALO; lo_exact = true; }
+                else if (pre.hdr == NONE || pre.hdr == INHDR) { lo = a; lo_exact = true; }     // (only before any header: malformed)
+                else {
+                    const int64_t ls = (int64_t)pre.hdr + 1 - (int64_t)tile_start;
+                    lo_exact = ls >= -(int64_t)halo;
+                    lo = lo_exact ? (int)ls : -(int)halo;
+                }
+                if (b - a <= SEG) walk<KW, MINI, W>(sb, S.lut, a, b, lo, lo_exact, P, acc, true, slow);
+                else { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; }
+            }
+        }
+        __syncthreads();
+        // ---- long lines: SEG-byte pieces shared by the whole CTA
+        const uint32_t n_long = min(S.n_long, (uint32_t)LONGMAX);
+        if (n_long) {
+            if (tid == 0) {
+                uint32_t s = 0;
+                for (uint32_t j = 0; j < n_long; j++) {
+                    const uint32_t i = S.long_line[j];
+                    const int a = line_start_rel(i), b = (i < Cs) ? (int)S.nl[i] : (int)avail;
+                    S.long_pref[j] = s; s += (uint32_t)(b - a + SEG - 1) / SEG;
+                }
+                S.long_pref[n_long] = s;
+            }
+            __syncthreads();
+            const uint32_t n_pieces = S.long_pref[n_long];
+            for (uint32_t pc = tid; pc < n_pieces; pc += NT) {
+                uint32_t j = 0;
+                while (j + 1 < n_long && S.long_pref[j + 1] <= pc) j++;
+                const uint32_t i = S.long_line[j];
+                const int la = line_start_rel(i), lb = (i < Cs) ? (int)S.nl[i] : (int)avail;
+                const int a = la + (int)(pc - S.long_pref[j]) * SEG, b = min(a + SEG, lb);
+                int lo; bool lo_exact;
+                if (!fasta) {
+                    if (i > 0 || line0_starts_here) { lo = la; lo_exact = true; }
+                    else {
+                        const uint64_t p1 = pre.last[0];
+                        const int64_t ls = (p1 == NONE ? 0 : (int64_t)p1 + 1) - (int64_t)tile_start;
+                        lo_exact = ls >= -(int64_t)halo; lo = lo_exact ? (int)ls : -(int)halo;
+                    }
+                } else {
+                    const uint32_t rs = S.rstart[i];
+                    if (rs) { lo = (int)rs - HALO; lo_exact = true; }
+                    else if (pre.hdr == NONE || pre.hdr == INHDR) { lo = la; lo_exact = true; }
+                    else {
+                        const int64_t ls = (int64_t)pre.hdr + 1 - (int64_t)tile_start;
+                        lo_exact = ls >= -(int64_t)halo; lo = lo_exact ? (int)ls : -(int)halo;
+                    }
+                }
+                walk<KW, MINI, W>(sb, S.lut, a, b, lo, lo_exact, P, acc, fasta, slow);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- P4: block reduction of the register tallies, 9 atomics per CTA
+    uint64_t v[9] = {acc.n_records, acc.n_bases, acc.n_kmers, acc.n_not_rc, acc.ksum_lo, acc.ksum_hi, acc.n_query, acc.n_mini, acc.msum};
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], d);
+        if (lane == 0) S.red[tid >> 5][q] = v[q];
+    }
+    slow = __reduce_or_sync(0xffffffffu, slow);
+    if (lane == 0 && slow) atomicOr(P.flags, slow);
+    __syncthreads();
+    if (tid < 9) {
+        uint64_t s = 0;
+        for (int wi = 0; wi < NT / 32; wi++) s += S.red[wi][tid];
+        if (s) atomicAdd(&P.tallies[tid], (unsigned long long)s);
+    }
+}
+
+// ---- end-of-stream rules, one thread (fastq.rs:337-356, fasta.rs:200-216,348-356) ----------------
+__global__ void k_finalize(const Params P) {
+    const SState st = *P.final_state;
+    uint32_t err = 0;
+    if (P.format == NTG_FMT_FASTQ) {
+        const uint32_t r = (uint32_t)(st.count & 3);
+        const bool have_complete = st.count >= 4;
+        uint64_t start = 0;
+        if (have_complete) start = st.last[r] + 1;                 // behind the 4th newline of the last complete record
+        auto trim = [&](uint64_t b, uint64_t e) { return (e > b && P.bytes[e - 1] == '\r') ? e - 1 : e; };
+        if (r == 3) {                                              // last record without trailing newline
+            const uint64_t seq = st.last[2] + 1, sep = st.last[1] + 1, qual = st.last[0] + 1, end = P.n;
+            if (P.bytes[start] != '@' || P.bytes[sep] != '+' || trim(seq, sep - 1) - seq != trim(qual, end) - qual) err = 1;
+            else atomicAdd(&P.tallies[0], 1ull);
+        } else {
+            uint64_t ls = start;
+            for (uint32_t i = 0; i <= r; i++) {                     // leftover must be empty / "\r" lines only
+                const uint64_t le = i < r ? st.last[r - 1 - i] : P.n;
+                const uint64_t len = le - ls;
+                if (len > 1 || (len == 1 && P.bytes[ls] != '\r')) err = 1;
+                ls = le + 1;
+            }
+        }
+    } else {
+        // FASTA: the last record needs a pushed newline (one that is not the final byte)
+        if (st.hdr == INHDR || st.hdr == NONE || st.hdr == P.n - 1) err = 1;
+        P.tallies[0] = st.n_starts;
+    }
+    if (err) atomicOr(P.flags, (uint32_t)FLAG_PARSE_ERROR);
+}
+
+// ---- exact fallback: one thread per parsed record walks its raw_seq from global memory ---------
+template <int KW, bool MINI>
+__global__ void __launch_bounds__(128) k_tally_records(const Params P, const ntg_record* __restrict__ recs, uint64_t n_recs) {
+    __shared__ uint8_t lut[256];
+    __shared__ uint64_t red[4][9];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { uint8_t c = c_ncls[i]; if (i == '\r' || i == '\n') c = 6; lut[i] = c; }
+    __syncthreads();
+    Acc acc; uint32_t slow = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_recs; r += (uint64_t)gridDim.x * blockDim.x) {
+        const ntg_record rec = recs[r];
+        acc.n_records++; acc.n_bases += rec.num_bases;
+        const uint8_t* base = P.bytes + rec.seq_b;
+        const uint64_t len = rec.seq_e - rec.seq_b;
+        for (uint64_t o = 0; o < len; o += 0x40000000ull) {          // int-sized windows (records beyond 1 GiB)
+            const uint64_t rem = len - o;
+            const uint64_t wlen = rem < 0x40000000ull ? rem : 0x40000000ull;
+            const int lo = o ? -0x100000 : 0;                         // warm-up room inside the same record
+            walk<KW, MINI, 0>(base + o, lut, 0, (int)wlen, lo, true, P, acc, false, slow);
+        }
+    }
+    uint64_t v[9] = {acc.n_records, acc.n_bases, acc.n_kmers, acc.n_not_rc, acc.ksum_lo, acc.ksum_hi, acc.n_query, acc.n_mini, acc.msum};
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], d);
+        if (lane == 0) red[threadIdx.x >> 5][q] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        uint64_t s = 0;
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); wi++) s += red[wi][threadIdx.x];
+        if (s) atomicAdd(&P.tallies[threadIdx.x], (unsigned long long)s);
+    }
+}
+}  // namespace fused

@@ -1,0 +1,185 @@
+// fused_host.cuh — host orchestration of the fused tallies path.  Part of the unity build.
+#pragma once
+#include "fused.cuh"
+#include "parse.cuh"
+
+struct FusedControl {           // device-resident control block, zeroed per call
+    unsigned long long tallies[16];
+    uint32_t flags;
+    uint32_t tickets[59];       // one ticket per kernel launch of a call (chunked feeds use several)
+};
+static_assert(sizeof(FusedControl) == 128 + 4 + 59 * 4, "layout");
+constexpr int FUSED_MAX_LAUNCHES = 59;
+
+struct FusedState {
+    fused::TileSlot* slots = nullptr; uint64_t slots_cap = 0;
+    FusedControl* ctrl = nullptr;
+    fused::SState* final_state = nullptr;
+    FusedControl* h_ctrl = nullptr;          // pinned
+    uint32_t epoch = 0;
+    int max_ctas = 0;
+    // pending call
+    bool pending = false;
+    fused::Params P{};
+    ntg_tally_config cfg{};
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_chunk[FUSED_MAX_LAUNCHES] = {};
+    uint8_t* feed_buf = nullptr; size_t feed_cap = 0;   // device staging for host feeds
+    const uint8_t* host_bytes = nullptr;                // when the call was fed from host memory
+};
+
+typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
+static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m) {
+    using namespace fused;
+    if (k > 32) return k_fused<2, false, 0>;
+    if (m == 0) return k_fused<1, false, 0>;
+    if (k - m + 1 == 11) return k_fused<1, true, 11>;
+    return k_fused<1, true, 0>;
+}
+
+static int fused_init(ntg_ctx* ctx) {
+    if (ctx->fused) return NTG_OK;
+    auto* st = new FusedState();
+    ctx->fused = st;
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->ctrl, sizeof(FusedControl)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->final_state, sizeof(fused::SState)));
+    NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_ctrl, sizeof(FusedControl)));
+    NTG_CUDA(ctx, cudaEventCreate(&st->ev_k0));
+    NTG_CUDA(ctx, cudaEventCreate(&st->ev_k1));
+    for (auto& e : st->ev_chunk) NTG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    fused_kernel_t ks[4] = {fused::k_fused<2, false, 0>, fused::k_fused<1, false, 0>, fused::k_fused<1, true, 11>, fused::k_fused<1, true, 0>};
+    int occ_min = 1 << 30;
+    for (auto kf : ks) {
+        NTG_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fused::Smem)));
+        int occ = 0;
+        NTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, fused::NT, sizeof(fused::Smem)));
+        if (occ < 1) return ntg_set_error(ctx, NTG_ECUDA, "fused kernel does not fit on an SM");
+        occ_min = occ < occ_min ? occ : occ_min;
+    }
+    st->max_ctas = occ_min * ctx->sm_count;     // persistent grid: every CTA resident (look-back needs forward progress)
+    return NTG_OK;
+}
+static void fused_destroy(ntg_ctx* ctx) {
+    FusedState* st = ctx->fused;
+    if (!st) return;
+    cudaFree(st->slots); cudaFree(st->ctrl); cudaFree(st->final_state); cudaFreeHost(st->h_ctrl); cudaFree(st->feed_buf);
+    if (st->ev_k0) cudaEventDestroy(st->ev_k0);
+    if (st->ev_k1) cudaEventDestroy(st->ev_k1);
+    for (auto& e : st->ev_chunk) if (e) cudaEventDestroy(e);
+    delete st; ctx->fused = nullptr;
+}
+
+static int check_tally_cfg(ntg_ctx* ctx, const ntg_tally_config* cfg) {
+    if (!cfg) return ntg_set_error(ctx, NTG_EINVAL, "null config");
+    if (cfg->k == 0 || cfg->k > 64) return ntg_set_error(ctx, NTG_EINVAL, "k must be in 1..64");
+    if (cfg->m && (cfg->k > 32 || cfg->m > cfg->k)) return ntg_set_error(ctx, NTG_EINVAL, "minimizers need 1 <= m <= k <= 32");
+    if (cfg->has_query)
+        for (uint32_t i = 0; i < cfg->k; i++)
+            if (host_luts().code[cfg->query[i]] > 3 || (cfg->query[i] & 0x20)) return ntg_set_error(ctx, NTG_EINVAL, "query must be k bases of ACGT");
+    return NTG_OK;
+}
+
+// Prepare a call over n device-resident bytes; launches nothing yet.
+static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg) {
+    NTG_TRY(fused_init(ctx));
+    FusedState* st = ctx->fused;
+    if (st->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is already pending: collect it first");
+    if ((reinterpret_cast<uintptr_t>(dbytes) & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
+    const uint64_t num_tiles = (n + fused::TILE - 1) / fused::TILE;
+    if (num_tiles > st->slots_cap) {
+        cudaFree(st->slots); st->slots = nullptr; st->slots_cap = 0;
+        NTG_CUDA(ctx, cudaMalloc((void**)&st->slots, num_tiles * sizeof(fused::TileSlot)));
+        NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, num_tiles * sizeof(fused::TileSlot), ctx->stream));
+        st->slots_cap = num_tiles; st->epoch = 0;
+    }
+    st->epoch++;
+    NTG_CUDA(ctx, cudaMemsetAsync(st->ctrl, 0, sizeof(FusedControl), ctx->stream));
+    fused::Params& P = st->P;
+    P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.ticket = nullptr;
+    P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
+    P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0;
+    P.q_lo = P.q_hi = 0;
+    if (cfg->has_query)
+        for (uint32_t i = 0; i < cfg->k; i++) {
+            P.q_hi = (P.q_hi << 2) | (P.q_lo >> 62);
+            P.q_lo = (P.q_lo << 2) | host_luts().code[cfg->query[i]];
+        }
+    st->cfg = *cfg;
+    st->pending = true;
+    return NTG_OK;
+}
+// Launch the fused kernel over tiles [tb, te) as launch number `li` of this call.
+static int fused_launch(ntg_ctx* ctx, uint64_t tb, uint64_t te, int li) {
+    FusedState* st = ctx->fused;
+    if (te <= tb) return NTG_OK;
+    uint64_t nt = te - tb;
+    unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
+    fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m);
+    kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
+    ctx->launches++;
+    NTG_CUDA(ctx, cudaGetLastError());
+    return NTG_OK;
+}
+static int fused_finish_enqueue(ntg_ctx* ctx) {
+    FusedState* st = ctx->fused;
+    fused::k_finalize<<<1, 1, 0, ctx->stream>>>(st->P);
+    ctx->launches++;
+    NTG_CUDA(ctx, cudaGetLastError());
+    NTG_CUDA(ctx, cudaMemcpyAsync(st->h_ctrl, st->ctrl, sizeof(FusedControl), cudaMemcpyDeviceToHost, ctx->stream));
+    return NTG_OK;
+}
+
+// forward: device-side parse used by the exact fallback (parse.cuh)
+static int run_parse_device(ntg_ctx* ctx, const uint8_t* host_bytes, const uint8_t* dbytes, size_t n, ntg_records** out,
+                            DevBuf<ntg_record>* keep_drecs);
+
+static void tallies_from_ctrl(const FusedControl* c, ntg_tallies* out) {
+    std::memset(out, 0, sizeof(*out));
+    out->n_records = c->tallies[0]; out->n_bases = c->tallies[1]; out->n_kmers = c->tallies[2]; out->n_not_rc = c->tallies[3];
+    out->kmer_sum_lo = c->tallies[4]; out->kmer_sum_hi = c->tallies[5]; out->n_query = c->tallies[6];
+    out->n_minimizers = c->tallies[7]; out->minimizer_sum = c->tallies[8];
+}
+
+static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, float* fused_kernel_ms) {
+    FusedState* st = ctx->fused;
+    if (!st || !st->pending) return ntg_set_error(ctx, NTG_EINVAL, "no pending tally call");
+    st->pending = false;
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (fused_kernel_ms) NTG_CUDA(ctx, cudaEventElapsedTime(fused_kernel_ms, st->ev_k0, st->ev_k1));
+    if (err) std::memset(err, 0, sizeof(*err));
+    if (err) err->format = st->P.format;
+    if (st->h_ctrl->flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
+
+    // ---- exact fallback: record table on the device, then one thread per delivered record
+    ntg_records* recs = nullptr;
+    DevBuf<ntg_record> drecs;
+    NTG_TRY(run_parse_device(ctx, st->host_bytes, st->P.bytes, st->P.n, &recs, &drecs));
+    if (err) *err = recs->error;
+    NTG_CUDA(ctx, cudaMemsetAsync(st->ctrl, 0, sizeof(FusedControl), ctx->stream));
+    if (recs->n_records) {
+        unsigned grid = (unsigned)((recs->n_records + 127) / 128);
+        if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
+        if (st->P.k > 32) fused::k_tally_records<2, false><<<grid, 128, 0, ctx->stream>>>(st->P, drecs.p, recs->n_records);
+        else if (st->P.m == 0) fused::k_tally_records<1, false><<<grid, 128, 0, ctx->stream>>>(st->P, drecs.p, recs->n_records);
+        else fused::k_tally_records<1, true><<<grid, 128, 0, ctx->stream>>>(st->P, drecs.p, recs->n_records);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (!e) e = cudaMemcpyAsync(st->h_ctrl, st->ctrl, sizeof(FusedControl), cudaMemcpyDeviceToHost, ctx->stream);
+    if (!e) e = cudaStreamSynchronize(ctx->stream);
+    ntg_records_free(recs);
+    if (e) return ntg_set_error(ctx, NTG_ECUDA, "fallback: %s", cudaGetErrorString(e));
+    tallies_from_ctrl(st->h_ctrl, out);
+    return NTG_OK;
+}
+
+static int sniff_format(ntg_ctx* ctx, uint8_t b0, size_t n, ntg_tallies* out, ntg_parse_error* err, int* format) {
+    // parse_fastx_reader / get_fastx_reader (parser/mod.rs:85-93,37-46)
+    *format = NTG_FMT_NONE;
+    (void)ctx;
+    if (n < 2) { if (out) std::memset(out, 0, sizeof(*out)); if (err) { std::memset(err, 0, sizeof(*err)); err->kind = NTG_EEMPTY_FILE; } return 1; }
+    if (b0 == '>') *format = NTG_FMT_FASTA;
+    else if (b0 == '@') *format = NTG_FMT_FASTQ;
+    else { if (out) std::memset(out, 0, sizeof(*out)); if (err) { std::memset(err, 0, sizeof(*err)); err->kind = NTG_EUNKNOWN_FORMAT; } return 1; }
+    return 0;
+}

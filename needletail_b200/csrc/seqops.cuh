@@ -1,0 +1,286 @@
+// seqops.cuh — batch form of the reference's `Sequence` trait (materialising paths).
+// One thread per input byte / per k-mer start; compaction through scan.cuh.  Inputs are a
+// CSR batch (concatenated bytes + offsets).  Part of the unity build (ntgpu.cu).
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace seqops {
+constexpr int BLOCK = 256;
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
+
+// largest s with offs[s] <= g  (offs has nseq+1 ascending entries, offs[nseq] > g)
+__device__ __forceinline__ uint32_t seq_of(const uint32_t* __restrict__ offs, uint32_t nseq, uint32_t g) {
+    uint32_t lo = 0, hi = nseq;   // invariant: offs[lo] <= g < offs[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(offs + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- normalize / strip_returns: flag + changed, then scatter ---------------------------------
+// mode 0/1: sequence::normalize(iupac = mode)  (src/sequence.rs:19-62)
+// mode 2  : Sequence::strip_returns            (src/sequence.rs:165-191)
+__device__ __forceinline__ uint8_t xform(uint8_t b, int mode) {
+    if (mode == 2) return (b == '\r' || b == '\n') ? 0 : b;
+    return __ldg(&c_norm[mode][b]);
+}
+__global__ void __launch_bounds__(BLOCK) k_xform_flags(const uint8_t* __restrict__ seqs, const uint32_t* __restrict__ offs,
+                                                       uint32_t nseq, uint32_t total, int mode,
+                                                       uint8_t* __restrict__ keep, uint8_t* __restrict__ changed) {
+    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= total) return;
+    uint8_t b = seqs[g], o = xform(b, mode);
+    keep[g] = o != 0;
+    if (o != b) changed[seq_of(offs, nseq, g)] = 1;   // benign race: everyone writes 1
+}
+__global__ void __launch_bounds__(BLOCK) k_xform_scatter(const uint8_t* __restrict__ seqs, uint32_t total, int mode,
+                                                         const uint32_t* __restrict__ idx, uint8_t* __restrict__ out) {
+    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= total) return;
+    uint8_t o = xform(seqs[g], mode);
+    if (o) out[idx[g]] = o;
+}
+__global__ void __launch_bounds__(BLOCK) k_gather_offsets(const uint32_t* __restrict__ offs, uint32_t nseq,
+                                                          const uint32_t* __restrict__ idx, uint64_t* __restrict__ out_offs) {
+    uint32_t s = blockIdx.x * BLOCK + threadIdx.x;
+    if (s <= nseq) out_offs[s] = idx[offs[s]];
+}
+
+// ---- reverse_complement / quality_mask --------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_revcomp(const uint8_t* __restrict__ seqs, const uint32_t* __restrict__ offs,
+                                                   uint32_t nseq, uint32_t total, uint8_t* __restrict__ out) {
+    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= total) return;
+    uint32_t s = seq_of(offs, nseq, g);
+    uint32_t b = offs[s], e = offs[s + 1];
+    out[b + (e - 1 - g)] = __ldg(&c_comp[seqs[g]]);      // complement(): src/sequence.rs:67-105
+}
+__global__ void __launch_bounds__(BLOCK) k_qmask(const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ quals,
+                                                 uint32_t total, uint8_t score, uint8_t* __restrict__ out) {
+    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g < total) out[g] = quals[g] < score ? (uint8_t)'N' : seqs[g];   // src/sequence.rs:280-297
+}
+
+// ---- k-mer start validity: window [g, g+k) inside its sequence and all good bases ------------
+// (the set of windows both CanonicalKmers, src/kmer.rs:84-129, and BitNuclKmer,
+//  src/bitkmer.rs:39-109, emit: every start whose k bytes are all in ACGTacgt)
+__global__ void __launch_bounds__(BLOCK) k_kmer_valid(const uint8_t* __restrict__ seqs, const uint32_t* __restrict__ offs,
+                                                      uint32_t nseq, uint32_t total, uint32_t k, uint8_t* __restrict__ valid) {
+    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= total) return;
+    uint32_t s = seq_of(offs, nseq, g);
+    uint32_t e = offs[s + 1];
+    uint8_t v = 0;
+    if (g + k <= e) {
+        v = 1;
+        for (uint32_t i = 0; i < k; i++)
+            if (__ldg(&c_code[seqs[g + i]]) > 3) { v = 0; break; }
+    }
+    valid[g] = v;
+}
+
+// mode 0: canonical_kmers (byte compare, ties -> rc, was_rc = 1; val = 2-bit pack of the chosen slice, k <= 64)
+// mode 1: bit_kmers(canonical = false)   mode 2: bit_kmers(canonical = true)   (k <= 32; ties -> original)
+// mode 3: bit minimizers (m)             (k <= 32)
+__global__ void __launch_bounds__(BLOCK) k_kmer_emit(const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ rcs,
+                                                     const uint32_t* __restrict__ offs, uint32_t nseq, uint32_t total,
+                                                     uint32_t k, uint32_t m, int mode,
+                                                     const uint8_t* __restrict__ valid, const uint32_t* __restrict__ idx,
+                                                     uint32_t* __restrict__ pos, uint8_t* __restrict__ was_rc,
+                                                     uint64_t* __restrict__ val_lo, uint64_t* __restrict__ val_hi) {
+    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= total || !valid[g]) return;
+    uint32_t s = seq_of(offs, nseq, g);
+    uint32_t b = offs[s], e = offs[s + 1];
+    uint32_t p = g - b, len = e - b;
+    uint32_t o = idx[g];
+    pos[o] = p;
+    if (mode == 0) {
+        // result = buffer[pos..pos+k]; rc_result = rc_buffer[len-pos-k .. len-pos]   (src/kmer.rs:121-123)
+        uint32_t rbase = b + (len - p - k);
+        bool lt = false;     // result < rc_result ?
+        for (uint32_t i = 0; i < k; i++) {
+            uint8_t f = seqs[g + i];
+            uint8_t r = rcs ? rcs[rbase + i] : __ldg(&c_comp[seqs[g + k - 1 - i]]);
+            if (f != r) { lt = f < r; break; }
+        }
+        bool rc = !lt;       // ties => rc slice, was_rc = true   (src/kmer.rs:124-128)
+        was_rc[o] = rc ? 1 : 0;
+        uint64_t hi = 0, lo = 0;
+        for (uint32_t i = 0; i < k; i++) {
+            uint8_t c = rc ? (rcs ? rcs[rbase + i] : __ldg(&c_comp[seqs[g + k - 1 - i]])) : seqs[g + i];
+            uint64_t code = __ldg(&c_code[c]) & 3;
+            hi = (hi << 2) | (lo >> 62);
+            lo = (lo << 2) | code;
+        }
+        val_lo[o] = lo;
+        if (val_hi) val_hi[o] = hi;
+    } else {
+        uint64_t v = 0;
+        for (uint32_t i = 0; i < k; i++) v = (v << 2) | (uint64_t)__ldg(&c_code[seqs[g + i]]);   // extend_kmer, bitkmer.rs:26-36
+        if (mode == 1) { val_lo[o] = v; was_rc[o] = 0; }
+        else if (mode == 2) {
+            uint64_t r = bit_rc(v, k);                    // canonical(): bitkmer.rs:136-143
+            bool rc = v > r;
+            val_lo[o] = rc ? r : v; was_rc[o] = rc ? 1 : 0;
+        } else {
+            val_lo[o] = bit_minimizer_slow(v, k, m);      // bitkmer.rs:146-162
+        }
+    }
+}
+
+// ---- element-wise BitKmer helpers -------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_bitkmer_elem(const uint64_t* __restrict__ in, size_t n, uint32_t k, uint32_t m, int mode,
+                                                        uint64_t* __restrict__ out, uint8_t* __restrict__ was_rc) {
+    size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = in[i];
+    if (mode == 0) out[i] = bit_rc(v, k);
+    else if (mode == 1) { uint64_t r = bit_rc(v, k); bool rc = v > r; out[i] = rc ? r : v; was_rc[i] = rc ? 1 : 0; }
+    else out[i] = bit_minimizer_slow(v, k, m);
+}
+}  // namespace seqops
+
+// ================================================================================== host side
+struct BatchOnDevice {
+    DevBuf<uint8_t> seqs;
+    DevBuf<uint32_t> offs;
+    uint32_t nseq = 0, total = 0;
+};
+static int upload_batch(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, BatchOnDevice& b) {
+    if (!offs || (n && !seqs && offs[n] > 0)) return ntg_set_error(ctx, NTG_EINVAL, "null batch pointer");
+    if (offs[0] != 0) return ntg_set_error(ctx, NTG_EINVAL, "offs[0] must be 0");
+    for (size_t i = 0; i < n; i++)
+        if (offs[i + 1] < offs[i]) return ntg_set_error(ctx, NTG_EINVAL, "offsets must be ascending");
+    uint64_t total = offs[n];
+    if (total >= 0xFFFFFFF0ull || n >= 0xFFFFFFF0ull)
+        return ntg_set_error(ctx, NTG_EUNSUPPORTED, "batch of %llu bytes: split batches at 4 GiB", (unsigned long long)total);
+    b.nseq = (uint32_t)n; b.total = (uint32_t)total;
+    if (b.seqs.alloc(total) != cudaSuccess || b.offs.alloc(n + 1) != cudaSuccess)
+        return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    std::vector<uint32_t> o32(n + 1);
+    for (size_t i = 0; i <= n; i++) o32[i] = (uint32_t)offs[i];
+    NTG_CUDA(ctx, cudaMemcpyAsync(b.seqs.p, seqs, total, cudaMemcpyHostToDevice, ctx->stream));
+    NTG_CUDA(ctx, cudaMemcpyAsync(b.offs.p, o32.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // o32 is a stack-scoped staging vector
+    return NTG_OK;
+}
+
+static int run_xform(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, int mode,
+                     uint8_t* out, uint64_t* out_offs, uint8_t* changed) {
+    using namespace seqops;
+    if (!out || !out_offs || !changed) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
+    BatchOnDevice b;
+    NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
+    DevBuf<uint8_t> keep, dout, dchg; DevBuf<uint32_t> idx, tmp; DevBuf<uint64_t> dooffs;
+    if (keep.alloc(b.total) || dout.alloc(b.total) || dchg.alloc(n) || idx.alloc((size_t)b.total + 1) ||
+        tmp.alloc(scan_tmp_count(b.total)) || dooffs.alloc(n + 1))
+        return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    NTG_CUDA(ctx, cudaMemsetAsync(dchg.p, 0, n ? n : 1, ctx->stream));
+    if (b.total) {
+        k_xform_flags<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, mode, keep.p, dchg.p);
+        ctx->launches++;
+    }
+    NTG_TRY(exclusive_scan_u8(ctx, keep.p, idx.p, b.total, tmp.p));
+    if (b.total) {
+        k_xform_scatter<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, b.total, mode, idx.p, dout.p);
+        ctx->launches++;
+    }
+    k_gather_offsets<<<grid_for(n + 1), BLOCK, 0, ctx->stream>>>(b.offs.p, b.nseq, idx.p, dooffs.p);
+    ctx->launches++;
+    NTG_CUDA(ctx, cudaGetLastError());
+    NTG_CUDA(ctx, cudaMemcpyAsync(out_offs, dooffs.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) NTG_CUDA(ctx, cudaMemcpyAsync(changed, dchg.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t out_total = out_offs[n];
+    if (out_total) NTG_CUDA(ctx, cudaMemcpy(out, dout.p, out_total, cudaMemcpyDeviceToHost));
+    return NTG_OK;
+}
+
+struct ItemsPriv {
+    PinBuf<uint64_t> item_offs, val_lo, val_hi;
+    PinBuf<uint32_t> pos;
+    PinBuf<uint8_t> was_rc;
+};
+
+// mode: 0 canonical_kmers, 1 bit_kmers, 2 bit_kmers canonical, 3 minimizers
+static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const uint64_t* offs, size_t n,
+                     uint32_t k, uint32_t m, int mode, ntg_items** out) {
+    using namespace seqops;
+    if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (k == 0) return ntg_set_error(ctx, NTG_EINVAL, "k must be >= 1 (k = 0 panics in the reference, src/kmer.rs:91)");
+    if (mode == 0 && k > 64) return ntg_set_error(ctx, NTG_EINVAL, "canonical_kmers: k <= 64 supported");
+    if (mode != 0 && k > 32) return ntg_set_error(ctx, NTG_EINVAL, "bit k-mers hold at most 32 bases (u64, src/bitkmer.rs:2-3)");
+    if (mode == 3 && (m == 0 || m > k)) return ntg_set_error(ctx, NTG_EINVAL, "minimizer needs 1 <= m <= k");
+    BatchOnDevice b;
+    NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
+    DevBuf<uint8_t> drc, valid, dwas; DevBuf<uint32_t> idx, tmp, dpos; DevBuf<uint64_t> dlo, dhi, dioffs;
+    if (rc) {
+        if (drc.alloc(b.total)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+        NTG_CUDA(ctx, cudaMemcpyAsync(drc.p, rc, b.total, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (valid.alloc(b.total) || idx.alloc((size_t)b.total + 1) || tmp.alloc(scan_tmp_count(b.total)) || dioffs.alloc(n + 1))
+        return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    if (b.total) {
+        k_kmer_valid<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, k, valid.p);
+        ctx->launches++;
+    }
+    NTG_TRY(exclusive_scan_u8(ctx, valid.p, idx.p, b.total, tmp.p));
+    k_gather_offsets<<<grid_for(n + 1), BLOCK, 0, ctx->stream>>>(b.offs.p, b.nseq, idx.p, dioffs.p);
+    ctx->launches++;
+    uint32_t n_items = 0;
+    NTG_CUDA(ctx, cudaMemcpyAsync(&n_items, idx.p + b.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool want_hi = (mode == 0 && k > 32), want_rc = (mode != 3);
+    if (dpos.alloc(n_items) || dlo.alloc(n_items) || (want_hi && dhi.alloc(n_items)) || dwas.alloc(n_items))
+        return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    if (b.total && n_items) {
+        k_kmer_emit<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, rc ? drc.p : nullptr, b.offs.p, b.nseq, b.total, k, m,
+                                                                 mode, valid.p, idx.p, dpos.p, dwas.p, dlo.p, want_hi ? dhi.p : nullptr);
+        ctx->launches++;
+    }
+    NTG_CUDA(ctx, cudaGetLastError());
+    auto* priv = new ItemsPriv();
+    auto* it = new ntg_items();
+    auto fail = [&](int st, const char* msg) { delete priv; delete it; return ntg_set_error(ctx, st, "%s", msg); };
+    if (priv->item_offs.alloc(n + 1) || priv->pos.alloc(n_items) || priv->val_lo.alloc(n_items) ||
+        (want_hi && priv->val_hi.alloc(n_items)) || (want_rc && priv->was_rc.alloc(n_items)))
+        return fail(NTG_ENOMEM, "pinned allocation failed");
+    cudaError_t e = cudaMemcpyAsync(priv->item_offs.p, dioffs.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (!e && n_items) {
+        e = cudaMemcpyAsync(priv->pos.p, dpos.p, (size_t)n_items * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!e) e = cudaMemcpyAsync(priv->val_lo.p, dlo.p, (size_t)n_items * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!e && want_hi) e = cudaMemcpyAsync(priv->val_hi.p, dhi.p, (size_t)n_items * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!e && want_rc) e = cudaMemcpyAsync(priv->was_rc.p, dwas.p, (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (!e) e = cudaStreamSynchronize(ctx->stream);
+    if (e) return fail(NTG_ECUDA, cudaGetErrorString(e));
+    it->n_seqs = n; it->n_items = n_items;
+    it->item_offs = priv->item_offs.p; it->pos = priv->pos.p;
+    it->was_rc = want_rc ? priv->was_rc.p : nullptr;
+    it->val_lo = priv->val_lo.p; it->val_hi = want_hi ? priv->val_hi.p : nullptr;
+    it->_priv = priv;
+    *out = it;
+    return NTG_OK;
+}
+
+static int run_bitkmer_elem(ntg_ctx* ctx, const uint64_t* in, size_t n, uint32_t k, uint32_t m, int mode, uint64_t* out, uint8_t* was_rc) {
+    using namespace seqops;
+    if (!in || !out || (mode == 1 && !was_rc)) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
+    if (k == 0 || k > 32) return ntg_set_error(ctx, NTG_EINVAL, "BitKmer needs 1 <= k <= 32 (src/bitkmer.rs:130)");
+    if (mode == 2 && (m == 0 || m > k)) return ntg_set_error(ctx, NTG_EINVAL, "minimizer needs 1 <= m <= k");
+    if (n == 0) return NTG_OK;
+    DevBuf<uint64_t> din, dout; DevBuf<uint8_t> dw;
+    if (din.alloc(n) || dout.alloc(n) || dw.alloc(n)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    NTG_CUDA(ctx, cudaMemcpyAsync(din.p, in, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_bitkmer_elem<<<grid_for(n), BLOCK, 0, ctx->stream>>>(din.p, n, k, m, mode, dout.p, dw.p);
+    ctx->launches++;
+    NTG_CUDA(ctx, cudaGetLastError());
+    NTG_CUDA(ctx, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mode == 1) NTG_CUDA(ctx, cudaMemcpyAsync(was_rc, dw.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NTG_OK;
+}
