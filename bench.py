@@ -190,7 +190,7 @@ def run_ours(args):
         t = ctx.tally_device_collect()
         kms = t.pop("fused_kernel_ms")
         err = t.pop("err_kind"); t.pop("err_line")
-        assert err is None, err
+        assert err is None and t.pop("fallback") == 0, (err, "the fused single-pass kernel must produce the tallies")
         if world > 1:
             t = shard.allreduce_tallies(t, ctx)          # ncclAllReduce(ncclUint64, ncclSum) through the C ABI
         return t, kms

@@ -196,7 +196,8 @@ typedef struct ntg_tallies {
     uint64_t n_query;
     uint64_t n_minimizers;     /* bit_kmers(k,false) items                               */
     uint64_t minimizer_sum;    /* wrapping sum of bitkmer::minimizer(kmer, m).0          */
-    uint64_t reserved[7];
+    uint64_t reserved[7];      /* reserved[0]: 0 = single-pass fused kernel produced these; else bitmask of why the exact
+                                  record-table path re-ran (1 parse error, 2 newline-dense tile, 4 whitespace run > halo) */
 } ntg_tallies;
 
 /* host bytes: H2D copies are pipelined with the kernel inside the call (the end-to-end path) */

@@ -333,6 +333,7 @@ class Context:
         d = {f: int(getattr(t, f)) for f in TALLY_FIELDS}
         d["err_kind"] = ERROR_KINDS.get(e.kind) if e.kind else None
         d["err_line"] = int(e.line)
+        d["fallback"] = int(t.reserved[0])      # 0: the single-pass fused kernel produced the tallies
         return d
 
     def tally(self, data, k, m=0, iupac=False, query=None):

@@ -148,7 +148,8 @@ static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, f
     if (fused_kernel_ms) NTG_CUDA(ctx, cudaEventElapsedTime(fused_kernel_ms, st->ev_k0, st->ev_k1));
     if (err) std::memset(err, 0, sizeof(*err));
     if (err) err->format = st->P.format;
-    if (st->h_ctrl->flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
+    const uint32_t fast_flags = st->h_ctrl->flags;
+    if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
 
     // ---- exact fallback: record table on the device, then one thread per delivered record
     ntg_records* recs = nullptr;
@@ -170,6 +171,7 @@ static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, f
     ntg_records_free(recs);
     if (e) return ntg_set_error(ctx, NTG_ECUDA, "fallback: %s", cudaGetErrorString(e));
     tallies_from_ctrl(st->h_ctrl, out);
+    out->reserved[0] = fast_flags;          // why the exact path ran: 1 parse error, 2 newline-dense tile, 4 whitespace run > halo
     return NTG_OK;
 }
 

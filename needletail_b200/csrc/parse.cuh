@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(BLOCK) k_fasta_records(const uint8_t* __restri
                                                          const uint32_t* __restrict__ stpos, uint32_t n_starts,
                                                          const uint32_t* __restrict__ nlidx, const uint32_t* __restrict__ cridx,
                                                          const uint32_t* __restrict__ nlpos, uint32_t n_nl,
-                                                         ntg_record* __restrict__ recs, uint32_t* __restrict__ last_bad) {
+                                                         ntg_record* __restrict__ recs, uint32_t* __restrict__ last_bad,
+                                                         uint32_t* __restrict__ first_le) {
     uint32_t r = blockIdx.x * BLOCK + threadIdx.x;
     if (r >= n_starts) return;
     uint32_t start = stpos[r];
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(BLOCK) k_fasta_records(const uint8_t* __restri
     o.num_bases = (uint64_t)(se - sb) - (nlidx[se] - nlidx[sb]) - (cridx[se] - cridx[sb]);   // fasta.rs:102-107
     o.line = 1 + (uint64_t)ord;
     recs[r] = o;
+    // line_ending(): taken from the first record whose all() contains a newline (fasta.rs:358-360, utils.rs:106-117)
+    if (first_nl < last) atomicMin(&first_le[0], r);
 }
 }  // namespace parse
 
@@ -185,8 +188,7 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
 
     DevBuf<ntg_record> drecs_own;
     DevBuf<ntg_record>& drecs = keep_drecs ? *keep_drecs : drecs_own;
-    uint64_t first_nl_of_first = ~0ull;
-    if (n_nl) { uint32_t v = 0; PCUDA(cudaMemcpy(&v, nlpos.p, 4, cudaMemcpyDeviceToHost)); first_nl_of_first = v; }
+    uint32_t le_rec = 0;     // index of the first record whose all() contains a newline (FASTQ: always record 0)
     if (!fasta) {
         // -------------------------------------------------------------------------- FASTQ
         uint32_t n_complete = n_nl / 4, rem = n_nl % 4;
@@ -267,14 +269,16 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         }
     } else {
         // -------------------------------------------------------------------------- FASTA
-        DevBuf<uint32_t> last_bad;
-        if (drecs.alloc(n_st) || last_bad.alloc(1)) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
+        DevBuf<uint32_t> last_bad, first_le;
+        if (drecs.alloc(n_st) || last_bad.alloc(1) || first_le.alloc(1)) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
         PCUDA(cudaMemsetAsync(last_bad.p, 0, 4, ctx->stream));
-        k_fasta_records<<<grid_for(n_st), BLOCK, 0, ctx->stream>>>(dbytes.p, n32, stpos.p, n_st, nlidx.p, cridx.p, nlpos.p, n_nl, drecs.p, last_bad.p);
+        PCUDA(cudaMemsetAsync(first_le.p, 0xFF, 4, ctx->stream));
+        k_fasta_records<<<grid_for(n_st), BLOCK, 0, ctx->stream>>>(dbytes.p, n32, stpos.p, n_st, nlidx.p, cridx.p, nlpos.p, n_nl, drecs.p, last_bad.p, first_le.p);
         ctx->launches++;
         PCUDA(cudaGetLastError());
         uint32_t bad = 0;
         PCUDA(cudaMemcpyAsync(&bad, last_bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PCUDA(cudaMemcpyAsync(&le_rec, first_le.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         PCUDA(cudaStreamSynchronize(ctx->stream));
         uint64_t total = n_st - (bad ? 1 : 0);
         if (priv->recs.alloc(n_st)) return done(ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed"));
@@ -292,6 +296,12 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
     }
 #undef PCUDA
 #undef PTRY
-    if (res->n_records) res->line_ending = host_line_ending(pk, res->records[0].start, res->records[0].all_e, first_nl_of_first);
+    if (le_rec < res->n_records) {
+        // the first newline inside that record is the one ending its header line
+        const ntg_record& lr = res->records[le_rec];
+        uint64_t q = lr.id_e;
+        if (pk.at(q) == '\r') q++;                               // id() had a '\r' trimmed
+        res->line_ending = host_line_ending(pk, lr.start, lr.all_e, q);
+    }
     return done(NTG_OK);
 }

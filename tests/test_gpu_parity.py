@@ -315,6 +315,7 @@ def test_synth_matches_oracle_and_tallies(ctx):
             e = O.tally_fastx(exp.tobytes(), k=31, m=21)
             for key in TALLY_KEYS:
                 assert t[key] == e[key], (n_thresh, key)
+            assert t["fallback"] == 0                      # the fused single-pass kernel, not the exact re-run
             if n_thresh == 0:
                 assert t["n_kmers"] == nrec * (L - 30) and t["n_bases"] == nrec * L
     finally:
@@ -331,8 +332,18 @@ def test_synth_matches_oracle_and_tallies(ctx):
         e = O.tally_fastx(exp.tobytes(), k=21, m=11)
         for key in TALLY_KEYS:
             assert t[key] == e[key], key
+        assert t["fallback"] == 0
     finally:
         ctx.device_free(d)
+
+
+def test_fast_path_is_taken_on_clean_files(ctx):
+    fx = load_fixtures()
+    assert ctx.tally(fx["data/28S.fasta"], k=31, m=21)["fallback"] == 0
+    assert ctx.tally(fx["data/PRJNA271013_head.fq"], k=31, m=21)["fallback"] == 0
+    assert ctx.tally(fx["data/PRJNA271013_head.fq"][:-1], k=51)["fallback"] == 0
+    assert ctx.tally(fx["data/bad_header.fastq"], k=4)["fallback"] & 1            # parse error -> exact path
+    assert ctx.tally(b">a\n" + b"A\n" * 60000, k=4)["fallback"] & 2               # newline-dense tile
 
 
 def test_shard_additivity_at_scale(ctx):
@@ -350,7 +361,7 @@ def test_shard_additivity_at_scale(ctx):
         b = ctx.tally_device(d, (nrec - half) * rb, k=31, m=21)
         for key in TALLY_KEYS[:-1]:
             assert (a[key] + b[key]) % 2**64 == whole[key], key
-        assert whole["n_records"] == nrec and whole["n_kmers"] == nrec * (L - 30)
+        assert whole["n_records"] == nrec and whole["n_kmers"] == nrec * (L - 30) and whole["fallback"] == 0
         host = ctx.d2h(d, (nrec - half) * rb)
         h = ctx.tally(host, k=31, m=21)                      # chunk-pipelined host feed
         for key in TALLY_KEYS:
