@@ -85,6 +85,7 @@ struct Params {
     uint32_t k, m, w;
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
     int has_query;
+    uint32_t one;                      // == 1 (run-time constant for mad.wide)
     uint64_t q_lo, q_hi;
 };
 
@@ -127,7 +128,8 @@ struct __align__(16) Smem {
     uint8_t tile[TILE];
     uint16_t nl[NLMAX + 8];            // sorted tile-relative newline offsets
     uint16_t rstart[NLMAX + 8];        // FASTA: per line, tile-relative (+HALO) start of its sequence region
-    uint8_t lut[256];                  // c_ncls (+ CR/LF split: 6)
+    uint8_t lut[256];                  // 0..3 ACGT, 4 kept non-ACGT, 0x85 deleted (space/tab), 0x86 deleted (\r \n)
+    uint32_t rins[256];                // fast walker: complement base pre-shifted into the high word of R
     uint64_t bar;
     uint32_t warp_tmp[NT / 32 + 2];
     uint64_t red[NT / 32][9];
@@ -175,23 +177,25 @@ __device__ __forceinline__ uint32_t block_incl_max(uint32_t v, uint32_t* tmp) { 
 //   KW   : 1 -> k <= 32 (u64 words), 2 -> k <= 64 (2 x u64)
 //   MINI : also bit_kmers(k,false) -> bitkmer::minimizer(m)      (KW == 1 only)
 //   W    : compile-time window k-m+1 (0 = run-time window, arrays indexed dynamically)
-template <int KW, bool MINI, int W>
-__device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int a, int b, int lo,
-                                     bool lo_exact, const Params& P, Acc& acc, bool count_bases, uint32_t& slow) {
-    const int k = (int)P.k;
-    // ---- warm-up: step back over at most k-1 kept good bases
-    int ws = a;
-    {
-        int got = 0, p = a - 1;
-        bool stopped = false;
-        while (p >= lo && got < k - 1) {
-            uint8_t c = lut[sb[p]];
-            if (c <= 3) { got++; ws = p; }
-            else if (c == 4) { stopped = true; break; }     // a non-ACGT base resets everything before it
-            p--;
-        }
-        if (!stopped && got < k - 1 && p < lo && !lo_exact) slow |= FLAG_HALO_OVERFLOW;
+// warm-up: step back from a over at most k-1 kept good bases, not below lo; returns where to start walking
+__device__ __forceinline__ int find_ws(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int a, int lo, bool lo_exact,
+                                       int k, uint32_t& slow) {
+    int ws = a, got = 0, p = a - 1;
+    bool stopped = false;
+    while (p >= lo && got < k - 1) {
+        const uint8_t c = lut[sb[p]];
+        if (c <= 3) { got++; ws = p; }
+        else if (c == 4) { stopped = true; break; }         // a non-ACGT base resets everything before it
+        p--;
     }
+    if (!stopped && got < k - 1 && p < lo && !lo_exact) slow |= FLAG_HALO_OVERFLOW;
+    return ws;
+}
+
+template <int KW, bool MINI, int W>
+__device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int ws, int a, int b,
+                                     const Params& P, Acc& acc, bool count_bases) {
+    const int k = (int)P.k;
     uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;              // forward / reverse-complement words (x1 = high word, KW == 2)
     int run = 0;
     const uint64_t kmask = (KW == 1) ? mask2k(P.k) : mask2k(P.k - 32);        // mask of the top word
@@ -212,9 +216,9 @@ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8
             do {                                             // fetch the next kept base
                 if (p >= b) return;
                 c = lut[sb[p]];
-                if (count_bases && p >= a && c != 6) acc.n_bases++;   // FASTA num_bases: everything but \r \n
+                if (count_bases && p >= a && c != 0x86) acc.n_bases++;   // FASTA num_bases: everything but \r \n
                 p++;
-            } while (c >= 5);
+            } while (c >= 0x80);
             const uint64_t code = c & 3;
             run = (c <= 3) ? run + 1 : 0;                    // a bad base (c == 4) still occupies a slot
             if (KW == 1) {
@@ -255,14 +259,153 @@ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8
     }
 }
 
+// =============================================================================== the fast walker
+// Constant-folded walker for the headline shapes (K, M compile-time, 17 <= K <= 31): the item bytes
+// sb[ws..b) must contain no deleted bytes (whitespace); if one shows up the function returns false
+// and the caller redoes the item with the generic walker above (acc is untouched in that case).
+//  - F / R are kept as explicit 32-bit word pairs (low-aligned, < 2^62);
+//  - every 64-bit "a < b" is ONE DSETP on the otherwise idle FP64 pipe: two non-negative integers
+//    below 2^62 order exactly like the doubles with the same bit patterns (finite, positive);
+//  - sums are carried as separate 64-bit sums of the low / high 32-bit words (IMAD.WIDE on the FMA
+//    pipe, no carry chains) and folded when the item ends;
+//  - non-ACGT bases never branch: they only push `next_ok`, the first index where a k-mer may end.
+struct FastLuts {
+    const uint8_t* cls;      // 0..3 code, 4 = kept non-ACGT, >= 0x80 = deleted byte
+    const uint32_t* rins;    // ((3 - code) << (2(K-1) - 32)) : the complement base entering the high word of R
+    uint32_t one;            // 1, as a run-time value (keeps mad.wide from being strength-reduced to IADD3 pairs)
+};
+__device__ __forceinline__ bool lt62(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
+    return __hiloint2double((int)ah, (int)al) < __hiloint2double((int)bh, (int)bl);
+}
+__device__ __forceinline__ void addw(uint64_t& acc, uint32_t v, uint32_t one) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(v), "r"(one));
+}
+
+template <int K, int M>
+__device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const FastLuts& L, int ws, int b, Acc& acc, const Params& P) {
+    static_assert(K >= 17 && K <= 31 && M >= 0 && M <= K, "fast walker shape");
+    constexpr bool MINI = M > 0;
+    constexpr int W = MINI ? K - M + 1 : 1;
+    constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
+    constexpr uint32_t KMASK_HI = (uint32_t)(KMASK >> 32);
+    constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
+    constexpr uint32_t MM_HI = (uint32_t)(MMASK >> 32), MM_LO = (uint32_t)MMASK, LM_HI = (uint32_t)(LMASK >> 32), LM_LO = (uint32_t)LMASK;
+    uint32_t fh = 0, fl = 0, rh = 0, rl = 0, seen = 0;
+    int next_ok = ws + K - 1;
+    uint64_t s_kl = 0, s_kh = 0, s_ml = 0, s_mh = 0;
+    uint32_t n_k = 0, n_nrc = 0, n_q = 0;
+    uint32_t cur_h[W + 1], cur_l[W + 1], suf_h[W + 1], suf_l[W + 1], pre_h = 0, pre_l = 0;
+#pragma unroll
+    for (int i = 0; i <= W; i++) { cur_h[i] = cur_l[i] = suf_h[i] = suf_l[i] = 0; }
+    const uint32_t one = L.one;
+    int p = ws;
+
+    auto roll = [&](int pp) {                       // consume byte pp: class, F, R, next_ok
+        const uint32_t byte = sb[pp];
+        const uint32_t c = L.cls[byte];
+        const uint32_t ri = L.rins[byte];
+        seen |= c;
+        if (c > 3) next_ok = pp + K;                  // a non-ACGT base: no k-mer may end before pp + K
+        fh = (__funnelshift_l(fl, fh, 2)) & KMASK_HI;
+        fl = (fl << 2) | (c & 3);
+        rl = __funnelshift_r(rl, rh, 2);
+        rh = (rh >> 2) | ri;
+    };
+    auto tally = [&](int pp, uint32_t wh, uint32_t wl) {   // k-mer ending at pp (if allowed) + its minimizer (wh:wl)
+        const bool emit = pp >= next_ok;
+        const bool lt = lt62(fh, fl, rh, rl);             // ties => was_rc = true (kmer.rs:124-128)
+        const uint32_t ch = lt ? fh : rh, cl = lt ? fl : rl;
+        if (emit) {
+            addw(s_kl, cl, one); addw(s_kh, ch, one);
+            n_k++;
+            n_nrc += lt ? 1u : 0u;
+            if (MINI) { addw(s_ml, wl, one); addw(s_mh, wh, one); }
+        }
+        if (P.has_query && emit && cl == (uint32_t)P.q_lo && ch == (uint32_t)(P.q_lo >> 32)) n_q++;
+    };
+
+    // phase 1: the first M-1 bases only feed F / R (no m-mer is complete, no k-mer can end)
+    {
+        const int e1 = min(b, ws + (MINI ? M - 1 : K - 1));
+        for (; p < e1; p++) roll(p);
+    }
+    // phase 2: van Herk blocks of W m-mer scores
+    while (p < b) {
+        const bool full = p + W <= b;
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            if (!full && p + i >= b) break;
+            roll(p + i);
+            uint32_t wh = 0, wl = 0;
+            if (MINI) {
+                // score of the m-mer ending here: min(x, RC_k(x)); x = F & MMASK, RC_k(x) = R | LMASK   (bitkmer.rs:146-162)
+                const uint32_t xh = fh & MM_HI, xl = fl & MM_LO, yh = rh | LM_HI, yl = rl | LM_LO;
+                const bool xlt = lt62(xh, xl, yh, yl);
+                const uint32_t sh = xlt ? xh : yh, sl = xlt ? xl : yl;
+                if (i == 0) { pre_h = sh; pre_l = sl; }
+                else { const bool q = lt62(sh, sl, pre_h, pre_l); pre_h = q ? sh : pre_h; pre_l = q ? sl : pre_l; }
+                cur_h[i] = sh; cur_l[i] = sl;
+                if (i == W - 1) { wh = pre_h; wl = pre_l; }
+                else { const bool q = lt62(suf_h[i + 1], suf_l[i + 1], pre_h, pre_l); wh = q ? suf_h[i + 1] : pre_h; wl = q ? suf_l[i + 1] : pre_l; }
+            }
+            tally(p + i, wh, wl);
+        }
+        p += W;
+        if (MINI && full) {
+            suf_h[W - 1] = cur_h[W - 1]; suf_l[W - 1] = cur_l[W - 1];
+#pragma unroll
+            for (int j = W - 2; j >= 1; j--) {       // suf[0] is never read
+                const bool q = lt62(cur_h[j], cur_l[j], suf_h[j + 1], suf_l[j + 1]);
+                suf_h[j] = q ? cur_h[j] : suf_h[j + 1]; suf_l[j] = q ? cur_l[j] : suf_l[j + 1];
+            }
+        }
+    }
+    if (seen & 0x80u) return false;                  // a deleted byte inside the item: not this walker's business
+    acc.n_kmers += n_k; acc.n_not_rc += n_nrc; acc.n_query += n_q;
+    acc.ksum_lo += s_kl + (s_kh << 32);
+    if (MINI) { acc.n_mini += n_k; acc.msum += s_ml + (s_mh << 32); }
+    return true;
+}
+
 // =============================================================================== the kernel
 __device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
     // global position -> byte, from shared memory when resident, else from global memory
     if (gpos + halo >= tile_start && gpos < tile_start + TILE) return sb[(int64_t)gpos - (int64_t)tile_start];
     return gpos < P.n ? P.bytes[gpos] : 0;
 }
+__device__ __forceinline__ uint8_t class_of(int i) {
+    uint8_t c = c_ncls[i];
+    if (c == 5) c = (i == '\r' || i == '\n') ? 0x86 : 0x85;
+    return c;
+}
 
 template <int KW, bool MINI, int W>
+__device__ __noinline__ void walk_slow(const uint8_t* sb, const uint8_t* lut, int ws, int a, int b, const Params& P, Acc& acc, bool count_bases) {
+    walk<KW, MINI, W>(sb, lut, ws, a, b, P, acc, count_bases);
+}
+
+// One sequence-line fragment sb[a..b): warm-up, then the constant-folded walker when this kernel has one
+// (FK > 0) and the item holds no deleted bytes, else the generic walker.
+template <int KW, bool MINI, int W, int FK, int FM>
+__device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, int a, int b, int lo, bool lo_exact,
+                                         const Params& P, Acc& acc, bool fasta, uint32_t& slow) {
+    if (b > a && sb[b - 1] == '\r') b--;                   // a trailing '\r' is deleted by normalize: nothing to walk
+    const bool had_cr_only = b <= a;
+    if (had_cr_only) return;
+    const int ws = find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
+    if (FK > 0) {
+        FastLuts L{lut, rins, (uint32_t)P.one};
+        if (walk_fast<(FK > 0 ? FK : 17), (FK > 0 ? FM : 0)>(sb, L, ws, b, acc, P)) {
+            if (fasta) acc.n_bases += (uint64_t)(b - a);   // no deleted bytes in [ws,b): every byte is a base
+            return;
+        }
+        walk_slow<KW, MINI, W>(sb, lut, ws, a, b, P, acc, fasta);
+    } else {
+        walk<KW, MINI, W>(sb, lut, ws, a, b, P, acc, fasta);
+    }
+}
+
+template <int KW, bool MINI, int W, int FK, int FM>
 __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -270,9 +413,9 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31;
     for (int i = tid; i < 256; i += NT) {
-        uint8_t c = c_ncls[i];
-        if (i == '\r' || i == '\n') c = 6;
+        const uint8_t c = class_of(i);
         S.lut[i] = c;
+        S.rins[i] = (FK >= 17) ? ((3u - (c & 3u)) << (2 * ((FK >= 17 ? FK : 17) - 1) - 32)) : 0u;
     }
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -337,6 +480,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
         const uint32_t Cs = overflow ? 0 : C;                          // lines are only interpreted when the list is complete
         // line i (0..Cs) spans (nl[i-1], nl[i]) ; helpers on tile-relative coordinates
         auto line_start_rel = [&](uint32_t i) -> int { return i ? (int)S.nl[i - 1] + 1 : 0; };   // for i == 0: start of the in-tile fragment
+        auto line_end_rel = [&](uint32_t i) -> int { return i < Cs ? (int)S.nl[i] : (int)avail; };
         const bool line0_starts_here = (t == 0) || (sb[-1] == '\n');
 
         // ---- P2b: FASTA start events that do not need the prefix
@@ -351,7 +495,6 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
         uint32_t last_start1 = 0, nstarts_tot = 0;
         if (fasta) {
             last_start1 = block_incl_max(my_last_start, S.warp_tmp);
-            // broadcast the block-wide max / sum through the last thread
             uint32_t tot; block_excl_scan(my_nstarts, &tot, S.warp_tmp); nstarts_tot = tot;
             if (tid == NT - 1) S.bcast[0] = (int32_t)last_start1;
             __syncthreads();
@@ -366,7 +509,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             if (fasta) {
                 agg.n_starts = nstarts_tot;
                 agg.first_nl = Cs ? tile_start + S.nl[0] : NONE;
-                if (last_start1) { const uint32_t L = last_start1 - 1; agg.hdr = (L < Cs) ? tile_start + S.nl[L] : INHDR; }
+                if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
             }
             TileSlot* slot = &P.slots[t];
             SState pre = identity_state();
@@ -391,6 +534,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             S.prefix = pre;
             if (t + 1 == P.num_tiles) *P.final_state = inc;
         }
+        if (tid == 0) S.n_long = 0;
         __syncthreads();
         const SState pre = S.prefix;
         // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
@@ -403,12 +547,31 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
             return (q > ls && byte_at(P, sb, tile_start, halo, q - 1) == '\r') ? 1u : 0u;
         };
+        // warm-up bound of a fragment of line i: the line start (FASTQ) / the sequence-region start (FASTA)
+        auto fastq_bound = [&](uint32_t i, int a, int& lo, bool& lo_exact) {
+            if (i > 0 || line0_starts_here) { lo = line_start_rel(i); lo_exact = true; (void)a; }
+            else {
+                const uint64_t p1 = pre.last[0];
+                const int64_t ls = (p1 == NONE ? 0 : (int64_t)p1 + 1) - (int64_t)tile_start;
+                lo_exact = ls >= -(int64_t)halo;
+                lo = lo_exact ? (int)ls : -(int)halo;
+            }
+        };
+        auto fasta_bound = [&](uint32_t i, int a, int& lo, bool& lo_exact) {
+            const uint32_t rs = S.rstart[i];
+            if (rs) { lo = (int)rs - HALO; lo_exact = true; }
+            else if (pre.hdr == NONE || pre.hdr == INHDR) { lo = a; lo_exact = true; }     // (only before any header: malformed)
+            else {
+                const int64_t ls = (int64_t)pre.hdr + 1 - (int64_t)tile_start;
+                lo_exact = ls >= -(int64_t)halo;
+                lo = lo_exact ? (int)ls : -(int)halo;
+            }
+        };
 
-        S.n_long = 0;
-        __syncthreads();
         if (!fasta) {
             // ---------------------------------------------------------------------------- FASTQ
             const uint32_t ord0 = (uint32_t)(pre.count & 3);
+            // (A) every line: start bytes, n_bases, record completion  (cheap, all lanes busy)
             for (uint32_t i = tid; i <= Cs; i += NT) {
                 const uint32_t role = (ord0 + i) & 3;                     // 0 header, 1 sequence, 2 separator, 3 quality
                 const int s = line_start_rel(i);
@@ -434,21 +597,16 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                         }
                     }
                 }
-                if (role == 1) {                                          // sequence-line fragment inside the tile
-                    const int a = s, b = (i < Cs) ? (int)S.nl[i] : (int)avail;
-                    if (b > a) {
-                        int lo; bool lo_exact;
-                        if (i > 0 || line0_starts_here) { lo = a; lo_exact = true; }
-                        else {
-                            const uint64_t p1 = pre.last[0];
-                            const int64_t ls = (p1 == NONE ? 0 : (int64_t)p1 + 1) - (int64_t)tile_start;
-                            lo_exact = ls >= -(int64_t)halo;
-                            lo = lo_exact ? (int)ls : -(int)halo;
-                        }
-                        if (b - a <= SEG) walk<KW, MINI, W>(sb, S.lut, a, b, lo, lo_exact, P, acc, false, slow);
-                        else { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; }
-                    }
-                }
+            }
+            // (B) sequence lines only: thread j walks the j-th role-1 line of the tile (every 4th line)
+            const uint32_t i_first = (1u - ord0) & 3u;
+            for (uint32_t i = i_first + 4u * tid; i <= Cs; i += 4u * NT) {
+                const int a = line_start_rel(i), b = line_end_rel(i);
+                if (b <= a) continue;
+                if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
+                int lo; bool lo_exact;
+                fastq_bound(i, a, lo, lo_exact);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, false, slow);
             }
         } else {
             // ---------------------------------------------------------------------------- FASTA
@@ -466,7 +624,6 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             const uint32_t incl = block_incl_max(lm, S.warp_tmp);
             uint32_t run = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) run = 0;
-            // exclusive value for this thread = inclusive value of the previous thread
             __shared__ uint32_t s_prev[NT / 32 + 1];
             if (lane == 31) s_prev[tid >> 5] = incl;
             __syncthreads();
@@ -478,19 +635,12 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             __syncthreads();
             for (uint32_t i = tid; i <= Cs; i += NT) {
                 if (is_header(i)) continue;
-                const int a = line_start_rel(i), b = (i < Cs) ? (int)S.nl[i] : (int)avail;
+                const int a = line_start_rel(i), b = line_end_rel(i);
                 if (b <= a) continue;
+                if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                 int lo; bool lo_exact;
-                const uint32_t rs = S.rstart[i];
-                if (rs) { lo = (int)rs - HALO; lo_exact = true; }
-                else if (pre.hdr == NONE || pre.hdr == INHDR) { lo = a; lo_exact = true; }     // (only before any header: malformed)
-                else {
-                    const int64_t ls = (int64_t)pre.hdr + 1 - (int64_t)tile_start;
-                    lo_exact = ls >= -(int64_t)halo;
-                    lo = lo_exact ? (int)ls : -(int)halo;
-                }
-                if (b - a <= SEG) walk<KW, MINI, W>(sb, S.lut, a, b, lo, lo_exact, P, acc, true, slow);
-                else { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; }
+                fasta_bound(i, a, lo, lo_exact);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, true, slow);
             }
         }
         __syncthreads();
@@ -498,13 +648,13 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
         const uint32_t n_long = min(S.n_long, (uint32_t)LONGMAX);
         if (n_long) {
             if (tid == 0) {
-                uint32_t s = 0;
+                // (order of long_line[] is arbitrary: atomics) -> prefix of piece counts
+                uint32_t sacc = 0;
                 for (uint32_t j = 0; j < n_long; j++) {
                     const uint32_t i = S.long_line[j];
-                    const int a = line_start_rel(i), b = (i < Cs) ? (int)S.nl[i] : (int)avail;
-                    S.long_pref[j] = s; s += (uint32_t)(b - a + SEG - 1) / SEG;
+                    S.long_pref[j] = sacc; sacc += (uint32_t)(line_end_rel(i) - line_start_rel(i) + SEG - 1) / SEG;
                 }
-                S.long_pref[n_long] = s;
+                S.long_pref[n_long] = sacc;
             }
             __syncthreads();
             const uint32_t n_pieces = S.long_pref[n_long];
@@ -512,26 +662,11 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                 uint32_t j = 0;
                 while (j + 1 < n_long && S.long_pref[j + 1] <= pc) j++;
                 const uint32_t i = S.long_line[j];
-                const int la = line_start_rel(i), lb = (i < Cs) ? (int)S.nl[i] : (int)avail;
+                const int la = line_start_rel(i), lb = line_end_rel(i);
                 const int a = la + (int)(pc - S.long_pref[j]) * SEG, b = min(a + SEG, lb);
                 int lo; bool lo_exact;
-                if (!fasta) {
-                    if (i > 0 || line0_starts_here) { lo = la; lo_exact = true; }
-                    else {
-                        const uint64_t p1 = pre.last[0];
-                        const int64_t ls = (p1 == NONE ? 0 : (int64_t)p1 + 1) - (int64_t)tile_start;
-                        lo_exact = ls >= -(int64_t)halo; lo = lo_exact ? (int)ls : -(int)halo;
-                    }
-                } else {
-                    const uint32_t rs = S.rstart[i];
-                    if (rs) { lo = (int)rs - HALO; lo_exact = true; }
-                    else if (pre.hdr == NONE || pre.hdr == INHDR) { lo = la; lo_exact = true; }
-                    else {
-                        const int64_t ls = (int64_t)pre.hdr + 1 - (int64_t)tile_start;
-                        lo_exact = ls >= -(int64_t)halo; lo = lo_exact ? (int)ls : -(int)halo;
-                    }
-                }
-                walk<KW, MINI, W>(sb, S.lut, a, b, lo, lo_exact, P, acc, fasta, slow);
+                if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, fasta, slow);
             }
         }
         __syncthreads();
@@ -549,9 +684,9 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
     if (lane == 0 && slow) atomicOr(P.flags, slow);
     __syncthreads();
     if (tid < 9) {
-        uint64_t s = 0;
-        for (int wi = 0; wi < NT / 32; wi++) s += S.red[wi][tid];
-        if (s) atomicAdd(&P.tallies[tid], (unsigned long long)s);
+        uint64_t sres = 0;
+        for (int wi = 0; wi < NT / 32; wi++) sres += S.red[wi][tid];
+        if (sres) atomicAdd(&P.tallies[tid], (unsigned long long)sres);
     }
 }
 
@@ -591,7 +726,7 @@ template <int KW, bool MINI>
 __global__ void __launch_bounds__(128) k_tally_records(const Params P, const ntg_record* __restrict__ recs, uint64_t n_recs) {
     __shared__ uint8_t lut[256];
     __shared__ uint64_t red[4][9];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { uint8_t c = c_ncls[i]; if (i == '\r' || i == '\n') c = 6; lut[i] = c; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = class_of(i);
     __syncthreads();
     Acc acc; uint32_t slow = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_recs; r += (uint64_t)gridDim.x * blockDim.x) {
@@ -603,7 +738,8 @@ __global__ void __launch_bounds__(128) k_tally_records(const Params P, const ntg
             const uint64_t rem = len - o;
             const uint64_t wlen = rem < 0x40000000ull ? rem : 0x40000000ull;
             const int lo = o ? -0x100000 : 0;                         // warm-up room inside the same record
-            walk<KW, MINI, 0>(base + o, lut, 0, (int)wlen, lo, true, P, acc, false, slow);
+            const int ws = find_ws(base + o, lut, 0, lo, true, (int)P.k, slow);
+            walk<KW, MINI, 0>(base + o, lut, ws, 0, (int)wlen, P, acc, false);
         }
     }
     uint64_t v[9] = {acc.n_records, acc.n_bases, acc.n_kmers, acc.n_not_rc, acc.ksum_lo, acc.ksum_hi, acc.n_query, acc.n_mini, acc.msum};

@@ -29,12 +29,19 @@ struct FusedState {
 };
 
 typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
+// kernel variants: three constant-folded headline shapes + the generic ones
+#define NTG_FUSED_KERNELS(X) \
+    X((k_fused<1, true, 11, 31, 21>)) X((k_fused<1, true, 11, 21, 11>)) X((k_fused<1, false, 0, 31, 0>)) \
+    X((k_fused<2, false, 0, 0, 0>)) X((k_fused<1, false, 0, 0, 0>)) X((k_fused<1, true, 11, 0, 0>)) X((k_fused<1, true, 0, 0, 0>))
 static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m) {
     using namespace fused;
-    if (k > 32) return k_fused<2, false, 0>;
-    if (m == 0) return k_fused<1, false, 0>;
-    if (k - m + 1 == 11) return k_fused<1, true, 11>;
-    return k_fused<1, true, 0>;
+    if (k == 31 && m == 21) return k_fused<1, true, 11, 31, 21>;
+    if (k == 21 && m == 11) return k_fused<1, true, 11, 21, 11>;
+    if (k == 31 && m == 0) return k_fused<1, false, 0, 31, 0>;
+    if (k > 32) return k_fused<2, false, 0, 0, 0>;
+    if (m == 0) return k_fused<1, false, 0, 0, 0>;
+    if (k - m + 1 == 11) return k_fused<1, true, 11, 0, 0>;
+    return k_fused<1, true, 0, 0, 0>;
 }
 
 static int fused_init(ntg_ctx* ctx) {
@@ -47,7 +54,10 @@ static int fused_init(ntg_ctx* ctx) {
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k0));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k1));
     for (auto& e : st->ev_chunk) NTG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    fused_kernel_t ks[4] = {fused::k_fused<2, false, 0>, fused::k_fused<1, false, 0>, fused::k_fused<1, true, 11>, fused::k_fused<1, true, 0>};
+    using namespace fused;
+#define NTG_X(k) (fused_kernel_t)k,
+    fused_kernel_t ks[] = {NTG_FUSED_KERNELS(NTG_X)};
+#undef NTG_X
     int occ_min = 1 << 30;
     for (auto kf : ks) {
         NTG_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fused::Smem)));
@@ -97,7 +107,7 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
     fused::Params& P = st->P;
     P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.ticket = nullptr;
     P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
-    P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0;
+    P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1;
     P.q_lo = P.q_hi = 0;
     if (cfg->has_query)
         for (uint32_t i = 0; i < cfg->k; i++) {
