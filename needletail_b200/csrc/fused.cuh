@@ -4,7 +4,7 @@
 //   + normalize (sequence.rs:19-62) + reverse_complement (sequence.rs:67-105,202-208)
 //   + CanonicalKmers (kmer.rs:84-129) + BitNuclKmer/minimizer (bitkmer.rs:26-162)
 //
-// Persistent CTAs claim 56 KiB tiles in order (atomic ticket).  Per tile:
+// Persistent CTAs claim 48 KiB tiles in order (atomic ticket).  Per tile:
 //   P0  the tile (+128 B back halo) is brought into shared memory by one cp.async.bulk (TMA 1-D
 //       bulk copy, SASS UBLKCP) completing on an mbarrier;
 //   P1  every thread scans one 256 B row for '\n' with 32-bit SIMD-in-register tests (rotated
@@ -23,10 +23,10 @@
 #include "common.cuh"
 
 namespace fused {
-constexpr int NT = 224;                  // 7 warps; 3 CTAs per SM
+constexpr int NT = 192;                  // 6 warps; 3 CTAs per SM (112 registers per thread)
 constexpr int ROWB = 256;                // bytes scanned per thread in P1
 constexpr int ROWW = ROWB / 4;
-constexpr int TILE = NT * ROWB;          // 57344
+constexpr int TILE = NT * ROWB;          // 49152
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
 constexpr int NLMAX = 3072;              // newline capacity per tile (mean line >= 18.7 B)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
@@ -274,30 +274,26 @@ struct FastLuts {
     const uint32_t* rins;    // ((3 - code) << (2(K-1) - 32)) : the complement base entering the high word of R
     uint32_t one;            // 1, as a run-time value (keeps mad.wide from being strength-reduced to IADD3 pairs)
 };
-__device__ __forceinline__ bool lt62(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
-    return __hiloint2double((int)ah, (int)al) < __hiloint2double((int)bh, (int)bl);
-}
-__device__ __forceinline__ void addw(uint64_t& acc, uint32_t v, uint32_t one) {
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(v), "r"(one));
-}
+__device__ __forceinline__ bool lt62(uint64_t a, uint64_t b) { return __longlong_as_double((long long)a) < __longlong_as_double((long long)b); }
+// exact double of a 32-bit word: (2^52 + v) - 2^52
+__device__ __forceinline__ double w2d(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 
 template <int K, int M>
-__device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const FastLuts& L, int ws, int b, Acc& acc, const Params& P) {
+__device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const FastLuts& L, int ws, int b, Acc& acc) {
     static_assert(K >= 17 && K <= 31 && M >= 0 && M <= K, "fast walker shape");
     constexpr bool MINI = M > 0;
     constexpr int W = MINI ? K - M + 1 : 1;
     constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
-    constexpr uint32_t KMASK_HI = (uint32_t)(KMASK >> 32);
     constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
-    constexpr uint32_t MM_HI = (uint32_t)(MMASK >> 32), MM_LO = (uint32_t)MMASK, LM_HI = (uint32_t)(LMASK >> 32), LM_LO = (uint32_t)LMASK;
-    uint32_t fh = 0, fl = 0, rh = 0, rl = 0, seen = 0;
+    uint64_t f = 0, r = 0;
+    uint32_t seen = 0;
     int next_ok = ws + K - 1;
-    uint64_t s_kl = 0, s_kh = 0, s_ml = 0, s_mh = 0;
-    uint32_t n_k = 0, n_nrc = 0, n_q = 0;
-    uint32_t cur_h[W + 1], cur_l[W + 1], suf_h[W + 1], suf_l[W + 1], pre_h = 0, pre_l = 0;
+    // tallies of this item as exact integer-valued doubles (< 2^53): they accumulate on the FP64 pipe
+    double d_kl = 0, d_kh = 0, d_ml = 0, d_mh = 0, d_nk = 0;
+    uint32_t n_nrc = 0;
+    uint64_t cur[W + 1], suf[W + 1], pre = 0;
 #pragma unroll
-    for (int i = 0; i <= W; i++) { cur_h[i] = cur_l[i] = suf_h[i] = suf_l[i] = 0; }
-    const uint32_t one = L.one;
+    for (int i = 0; i <= W; i++) { cur[i] = 0; suf[i] = 0; }
     int p = ws;
 
     auto roll = [&](int pp) {                       // consume byte pp: class, F, R, next_ok
@@ -306,22 +302,19 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
         const uint32_t ri = L.rins[byte];
         seen |= c;
         if (c > 3) next_ok = pp + K;                  // a non-ACGT base: no k-mer may end before pp + K
-        fh = (__funnelshift_l(fl, fh, 2)) & KMASK_HI;
-        fl = (fl << 2) | (c & 3);
-        rl = __funnelshift_r(rl, rh, 2);
-        rh = (rh >> 2) | ri;
+        f = ((f << 2) | (uint64_t)(c & 3)) & KMASK;
+        r = (r >> 2) | ((uint64_t)ri << 32);
     };
-    auto tally = [&](int pp, uint32_t wh, uint32_t wl) {   // k-mer ending at pp (if allowed) + its minimizer (wh:wl)
+    auto tally = [&](int pp, uint64_t win) {         // k-mer ending at pp (if allowed) + its minimizer
         const bool emit = pp >= next_ok;
-        const bool lt = lt62(fh, fl, rh, rl);             // ties => was_rc = true (kmer.rs:124-128)
-        const uint32_t ch = lt ? fh : rh, cl = lt ? fl : rl;
+        const bool lt = lt62(f, r);                     // ties => was_rc = true (kmer.rs:124-128)
+        const uint64_t c = lt ? f : r;
         if (emit) {
-            addw(s_kl, cl, one); addw(s_kh, ch, one);
-            n_k++;
+            d_kl += w2d((uint32_t)c); d_kh += w2d((uint32_t)(c >> 32));
+            d_nk += 1.0;
             n_nrc += lt ? 1u : 0u;
-            if (MINI) { addw(s_ml, wl, one); addw(s_mh, wh, one); }
+            if (MINI) { d_ml += w2d((uint32_t)win); d_mh += w2d((uint32_t)(win >> 32)); }
         }
-        if (P.has_query && emit && cl == (uint32_t)P.q_lo && ch == (uint32_t)(P.q_lo >> 32)) n_q++;
     };
 
     // phase 1: the first M-1 bases only feed F / R (no m-mer is complete, no k-mer can end)
@@ -336,34 +329,29 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
         for (int i = 0; i < W; i++) {
             if (!full && p + i >= b) break;
             roll(p + i);
-            uint32_t wh = 0, wl = 0;
+            uint64_t win = 0;
             if (MINI) {
                 // score of the m-mer ending here: min(x, RC_k(x)); x = F & MMASK, RC_k(x) = R | LMASK   (bitkmer.rs:146-162)
-                const uint32_t xh = fh & MM_HI, xl = fl & MM_LO, yh = rh | LM_HI, yl = rl | LM_LO;
-                const bool xlt = lt62(xh, xl, yh, yl);
-                const uint32_t sh = xlt ? xh : yh, sl = xlt ? xl : yl;
-                if (i == 0) { pre_h = sh; pre_l = sl; }
-                else { const bool q = lt62(sh, sl, pre_h, pre_l); pre_h = q ? sh : pre_h; pre_l = q ? sl : pre_l; }
-                cur_h[i] = sh; cur_l[i] = sl;
-                if (i == W - 1) { wh = pre_h; wl = pre_l; }
-                else { const bool q = lt62(suf_h[i + 1], suf_l[i + 1], pre_h, pre_l); wh = q ? suf_h[i + 1] : pre_h; wl = q ? suf_l[i + 1] : pre_l; }
+                const uint64_t x = f & MMASK, y = r | LMASK;
+                const uint64_t sc = lt62(x, y) ? x : y;
+                pre = (i == 0) ? sc : (lt62(sc, pre) ? sc : pre);
+                cur[i] = sc;
+                win = (i == W - 1) ? pre : (lt62(suf[i + 1], pre) ? suf[i + 1] : pre);
             }
-            tally(p + i, wh, wl);
+            tally(p + i, win);
         }
         p += W;
         if (MINI && full) {
-            suf_h[W - 1] = cur_h[W - 1]; suf_l[W - 1] = cur_l[W - 1];
+            suf[W - 1] = cur[W - 1];
 #pragma unroll
-            for (int j = W - 2; j >= 1; j--) {       // suf[0] is never read
-                const bool q = lt62(cur_h[j], cur_l[j], suf_h[j + 1], suf_l[j + 1]);
-                suf_h[j] = q ? cur_h[j] : suf_h[j + 1]; suf_l[j] = q ? cur_l[j] : suf_l[j + 1];
-            }
+            for (int j = W - 2; j >= 1; j--) suf[j] = lt62(cur[j], suf[j + 1]) ? cur[j] : suf[j + 1];     // suf[0] is never read
         }
     }
     if (seen & 0x80u) return false;                  // a deleted byte inside the item: not this walker's business
-    acc.n_kmers += n_k; acc.n_not_rc += n_nrc; acc.n_query += n_q;
-    acc.ksum_lo += s_kl + (s_kh << 32);
-    if (MINI) { acc.n_mini += n_k; acc.msum += s_ml + (s_mh << 32); }
+    const uint64_t nk = (uint64_t)d_nk;
+    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
+    acc.ksum_lo += (uint64_t)d_kl + ((uint64_t)d_kh << 32);
+    if (MINI) { acc.n_mini += nk; acc.msum += (uint64_t)d_ml + ((uint64_t)d_mh << 32); }
     return true;
 }
 
@@ -395,7 +383,7 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
     const int ws = find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
     if (FK > 0) {
         FastLuts L{lut, rins, (uint32_t)P.one};
-        if (walk_fast<(FK > 0 ? FK : 17), (FK > 0 ? FM : 0)>(sb, L, ws, b, acc, P)) {
+        if (walk_fast<(FK > 0 ? FK : 17), (FK > 0 ? FM : 0)>(sb, L, ws, b, acc)) {
             if (fasta) acc.n_bases += (uint64_t)(b - a);   // no deleted bytes in [ws,b): every byte is a base
             return;
         }

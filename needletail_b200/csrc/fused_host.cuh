@@ -33,8 +33,13 @@ typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64
 #define NTG_FUSED_KERNELS(X) \
     X((k_fused<1, true, 11, 31, 21>)) X((k_fused<1, true, 11, 21, 11>)) X((k_fused<1, false, 0, 31, 0>)) \
     X((k_fused<2, false, 0, 0, 0>)) X((k_fused<1, false, 0, 0, 0>)) X((k_fused<1, true, 11, 0, 0>)) X((k_fused<1, true, 0, 0, 0>))
-static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m) {
+static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) {
     using namespace fused;
+    if (has_query) {                           // the query count lives in the generic walkers only
+        if (k > 32) return k_fused<2, false, 0, 0, 0>;
+        if (m == 0) return k_fused<1, false, 0, 0, 0>;
+        return (k - m + 1 == 11) ? k_fused<1, true, 11, 0, 0> : k_fused<1, true, 0, 0, 0>;
+    }
     if (k == 31 && m == 21) return k_fused<1, true, 11, 31, 21>;
     if (k == 21 && m == 11) return k_fused<1, true, 11, 21, 11>;
     if (k == 31 && m == 0) return k_fused<1, false, 0, 31, 0>;
@@ -124,7 +129,7 @@ static int fused_launch(ntg_ctx* ctx, uint64_t tb, uint64_t te, int li) {
     if (te <= tb) return NTG_OK;
     uint64_t nt = te - tb;
     unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
-    fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m);
+    fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m, st->P.has_query != 0);
     kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
     ctx->launches++;
     NTG_CUDA(ctx, cudaGetLastError());
