@@ -24,9 +24,10 @@
 
 namespace fused {
 constexpr int NT = 192;                  // 6 warps; 3 CTAs per SM (112 registers per thread)
-constexpr int ROWB = 256;                // bytes scanned per thread in P1
+constexpr int ROWB = 256;                // P1 scans the tile in 256 B rows, one row per thread per round
 constexpr int ROWW = ROWB / 4;
-constexpr int TILE = NT * ROWB;          // 49152
+constexpr int TILE = 59 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
+constexpr int MAXROUNDS = (TILE / ROWB + NT - 1) / NT;   // 2
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
 constexpr int NLMAX = 3072;              // newline capacity per tile (mean line >= 18.7 B)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
@@ -83,6 +84,7 @@ struct Params {
     uint32_t* flags;
     SState* final_state;
     uint32_t k, m, w;
+    uint32_t tile_bytes;               // multiple of 256, <= TILE: sized so one tile holds about NT sequence lines
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
     int has_query;
     uint32_t one;                      // == 1 (run-time constant for mad.wide)
@@ -358,7 +360,7 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
 // =============================================================================== the kernel
 __device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
     // global position -> byte, from shared memory when resident, else from global memory
-    if (gpos + halo >= tile_start && gpos < tile_start + TILE) return sb[(int64_t)gpos - (int64_t)tile_start];
+    if (gpos + halo >= tile_start && gpos < tile_start + P.tile_bytes) return sb[(int64_t)gpos - (int64_t)tile_start];
     return gpos < P.n ? P.bytes[gpos] : 0;
 }
 __device__ __forceinline__ uint8_t class_of(int i) {
@@ -417,8 +419,9 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
         __syncthreads();
         const uint64_t t = tile_begin + S.tile_idx;
         if (t >= tile_end) break;
-        const uint64_t tile_start = t * (uint64_t)TILE;
-        const uint32_t avail = (uint32_t)min((uint64_t)TILE, P.n - tile_start);
+        const uint32_t TB = P.tile_bytes;
+        const uint64_t tile_start = t * (uint64_t)TB;
+        const uint32_t avail = (uint32_t)min((uint64_t)TB, P.n - tile_start);
         const uint32_t halo = t > 0 ? HALO : 0;
         const uint32_t bulk = avail & ~15u;
 
@@ -427,41 +430,57 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             mbar_expect_tx(&S.bar, halo + bulk);
             bulk_g2s(S.halo + (HALO - halo), P.bytes + tile_start - halo, halo + bulk, &S.bar);
         }
-        if (avail < TILE) for (uint32_t i = bulk + tid; i < TILE; i += NT) S.tile[i] = i < avail ? P.bytes[tile_start + i] : 0;
+        if (avail < TB) for (uint32_t i = bulk + tid; i < TB; i += NT) S.tile[i] = i < avail ? P.bytes[tile_start + i] : 0;
         if (t == 0) for (int i = tid; i < HALO; i += NT) S.halo[i] = 0;
         if (halo + bulk) { mbar_wait(&S.bar, parity); parity ^= 1; }
         __syncthreads();
 
-        // ---- P1: newline scan of this thread's 256 B row (rotated word order: conflict-free LDS.32)
-        uint32_t cnt = 0;
-        uint64_t wmask = 0;
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + tid * ROWW;
+        // ---- P1: newline scan, 256 B rows, row = round * NT + tid (rotated word order: conflict-free LDS.32)
+        const uint32_t nrows = TB / ROWB;
+        uint32_t cnt[MAXROUNDS];
+        uint64_t wmask[MAXROUNDS];
+#pragma unroll
+        for (int rd = 0; rd < MAXROUNDS; rd++) {
+            cnt[rd] = 0; wmask[rd] = 0;
+            const uint32_t rowi = rd * NT + tid;
+            if (rowi < nrows) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW;
 #pragma unroll 8
-        for (int j = 0; j < ROWW; j++) {
-            const uint32_t jj = (j + lane) & (ROWW - 1);
-            const uint32_t x = row[jj] ^ 0x0A0A0A0Au;
-            if ((x - 0x01010101u) & ~x & 0x80808080u) {             // exact as a boolean: some byte is '\n'
-                wmask |= 1ull << jj;
-                uint32_t z = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                z = ~(z | x | 0x7F7F7F7Fu);                          // 0x80 in every byte that is exactly '\n'
-                cnt += __popc(z);
+                for (int j = 0; j < ROWW; j++) {
+                    const uint32_t jj = (j + lane) & (ROWW - 1);
+                    const uint32_t x = row[jj] ^ 0x0A0A0A0Au;
+                    if ((x - 0x01010101u) & ~x & 0x80808080u) {             // exact as a boolean: some byte is '\n'
+                        wmask[rd] |= 1ull << jj;
+                        uint32_t z = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                        z = ~(z | x | 0x7F7F7F7Fu);                          // 0x80 in every byte that is exactly '\n'
+                        cnt[rd] += __popc(z);
+                    }
+                }
             }
         }
-        // ---- P2: ordered newline list
-        uint32_t C;
-        const uint32_t off = block_excl_scan(cnt, &C, S.warp_tmp);
+        // ---- P2: ordered newline list (rows are ordered round-major: one scan of the packed per-round counts)
+        static_assert(MAXROUNDS == 2, "packed scan below assumes two rounds");
+        uint32_t Cpacked;
+        const uint32_t offp = block_excl_scan(cnt[0] | (cnt[1] << 16), &Cpacked, S.warp_tmp);
+        const uint32_t C0 = Cpacked & 0xFFFFu, C = C0 + (Cpacked >> 16);
         const bool overflow = C > NLMAX;
         if (overflow) slow |= FLAG_NL_OVERFLOW;
-        if (!overflow && cnt) {
-            uint32_t o = off;
-            uint64_t mk = wmask;
-            while (mk) {
-                const int jj = __ffsll((long long)mk) - 1;
-                mk &= mk - 1;
-                const uint32_t wv = row[jj];
+        if (!overflow) {
 #pragma unroll
-                for (int bsel = 0; bsel < 4; bsel++)
-                    if (((wv >> (8 * bsel)) & 0xFF) == '\n') S.nl[o++] = (uint16_t)(tid * ROWB + jj * 4 + bsel);
+            for (int rd = 0; rd < MAXROUNDS; rd++) {
+                if (!cnt[rd]) continue;
+                const uint32_t rowi = rd * NT + tid;
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW;
+                uint32_t o = rd == 0 ? (offp & 0xFFFFu) : C0 + (offp >> 16);
+                uint64_t mk = wmask[rd];
+                while (mk) {
+                    const int jj = __ffsll((long long)mk) - 1;
+                    mk &= mk - 1;
+                    const uint32_t wv = row[jj];
+#pragma unroll
+                    for (int bsel = 0; bsel < 4; bsel++)
+                        if (((wv >> (8 * bsel)) & 0xFF) == '\n') S.nl[o++] = (uint16_t)(rowi * ROWB + jj * 4 + bsel);
+                }
             }
         }
         __syncthreads();

@@ -95,12 +95,34 @@ static int check_tally_cfg(ntg_ctx* ctx, const ntg_tally_config* cfg) {
 }
 
 // Prepare a call over n device-resident bytes; launches nothing yet.
-static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg) {
+// Tile size: about NT sequence lines per tile, so that every walker thread gets exactly one line.
+// `sample` = the first bytes of the input (host copy), used to estimate the line period.
+static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
+    size_t nl = 0;
+    for (size_t i = 0; i < ns; i++) nl += sample[i] == '\n';
+    double seqline_period;                       // bytes of input per sequence line
+    if (nl < 8) return fused::TILE;              // long lines: they are cut into SEG-byte pieces anyway
+    if (format == NTG_FMT_FASTQ) seqline_period = 4.0 * (double)ns / (double)nl;
+    else {
+        size_t hdr = 0;
+        for (size_t i = 0; i + 1 < ns; i++) hdr += (sample[i] == '\n' && sample[i + 1] == '>');
+        size_t seql = nl > hdr ? nl - hdr : 1;
+        seqline_period = (double)ns / (double)seql;
+        if ((double)ns / (double)nl > fused::SEG) return fused::TILE;
+    }
+    double want = 0.97 * fused::NT * seqline_period;
+    uint32_t tb = (uint32_t)(want / 256.0) * 256u;
+    if (tb < 16384u) tb = 16384u;
+    if (tb > (uint32_t)fused::TILE) tb = fused::TILE;
+    return tb;
+}
+
+static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes) {
     NTG_TRY(fused_init(ctx));
     FusedState* st = ctx->fused;
     if (st->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is already pending: collect it first");
     if ((reinterpret_cast<uintptr_t>(dbytes) & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
-    const uint64_t num_tiles = (n + fused::TILE - 1) / fused::TILE;
+    const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
     if (num_tiles > st->slots_cap) {
         cudaFree(st->slots); st->slots = nullptr; st->slots_cap = 0;
         NTG_CUDA(ctx, cudaMalloc((void**)&st->slots, num_tiles * sizeof(fused::TileSlot)));
@@ -112,7 +134,7 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
     fused::Params& P = st->P;
     P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.ticket = nullptr;
     P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
-    P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1;
+    P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
     P.q_lo = P.q_hi = 0;
     if (cfg->has_query)
         for (uint32_t i = 0; i < cfg->k; i++) {

@@ -253,12 +253,16 @@ int ntg_tally_fastx_device_enqueue(ntg_ctx* ctx, uint64_t dptr, size_t n, const 
     NTG_TRY(fused_init(ctx));
     FusedState* st = ctx->fused;
     if (n < 2 || !dptr) return ntg_set_error(ctx, NTG_EINVAL, "enqueue needs >= 2 device-resident bytes (use ntg_tally_fastx_device for the sniff rules)");
-    uint8_t b0 = 0;
-    NTG_CUDA(ctx, cudaMemcpyAsync(&b0, (const void*)(uintptr_t)dptr, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    // sniff + tile sizing from the first 64 KiB (one small D2H; the stream is otherwise untouched)
+    static thread_local std::vector<uint8_t> sample;
+    const size_t ns = n < 65536 ? n : 65536;
+    sample.resize(ns);
+    NTG_CUDA(ctx, cudaMemcpyAsync(sample.data(), (const void*)(uintptr_t)dptr, ns, cudaMemcpyDeviceToHost, ctx->stream));
     NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint8_t b0 = sample[0];
     int format = b0 == '>' ? NTG_FMT_FASTA : (b0 == '@' ? NTG_FMT_FASTQ : NTG_FMT_NONE);
     if (format == NTG_FMT_NONE) return ntg_set_error(ctx, NTG_EUNKNOWN_FORMAT, "first byte is neither '>' nor '@'");
-    NTG_TRY(fused_begin(ctx, (const uint8_t*)(uintptr_t)dptr, n, format, cfg));
+    NTG_TRY(fused_begin(ctx, (const uint8_t*)(uintptr_t)dptr, n, format, cfg, pick_tile_bytes(sample.data(), ns, format)));
     st->host_bytes = nullptr;
     NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
     int s = fused_launch(ctx, 0, st->P.num_tiles, 0);
@@ -303,11 +307,12 @@ int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tall
         if (cudaMalloc((void**)&st->feed_buf, cap) != cudaSuccess) { cudaGetLastError(); return ntg_set_error(ctx, NTG_ENOMEM, "cudaMalloc(%zu) failed", cap); }
         st->feed_cap = cap;
     }
-    NTG_TRY(fused_begin(ctx, st->feed_buf, n, format, cfg));
+    const uint32_t tile_bytes = pick_tile_bytes(bytes, n < 65536 ? n : 65536, format);
+    NTG_TRY(fused_begin(ctx, st->feed_buf, n, format, cfg, tile_bytes));
     st->host_bytes = bytes;
     // chunk size: a multiple of the tile, at most FUSED_MAX_LAUNCHES chunks
     const uint64_t num_tiles = st->P.num_tiles;
-    uint64_t tiles_per_chunk = ((size_t(256) << 20) + fused::TILE - 1) / fused::TILE;
+    uint64_t tiles_per_chunk = ((size_t(256) << 20) + tile_bytes - 1) / tile_bytes;
     if ((num_tiles + tiles_per_chunk - 1) / tiles_per_chunk > FUSED_MAX_LAUNCHES)
         tiles_per_chunk = (num_tiles + FUSED_MAX_LAUNCHES - 1) / FUSED_MAX_LAUNCHES;
     // the copy stream must not overwrite feed_buf while an earlier call's kernels still read it, and the
@@ -320,7 +325,7 @@ int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tall
     int li = 0;
     for (uint64_t tb = 0; tb < num_tiles && !e && s == NTG_OK; tb += tiles_per_chunk, li++) {
         const uint64_t te = tb + tiles_per_chunk < num_tiles ? tb + tiles_per_chunk : num_tiles;
-        const size_t b0 = tb * fused::TILE, b1 = te * (uint64_t)fused::TILE < n ? te * (uint64_t)fused::TILE : n;
+        const size_t b0 = tb * (uint64_t)tile_bytes, b1 = te * (uint64_t)tile_bytes < n ? te * (uint64_t)tile_bytes : n;
         e = cudaMemcpyAsync(st->feed_buf + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream);
         if (!e) e = cudaEventRecord(st->ev_chunk[li], ctx->copy_stream);
         if (!e) e = cudaStreamWaitEvent(ctx->stream, st->ev_chunk[li], 0);
