@@ -368,3 +368,17 @@ def test_shard_additivity_at_scale(ctx):
             assert h[key] == b[key], key
     finally:
         ctx.device_free(d)
+
+
+def test_cpp_host_mirror(tmp_path):
+    """The C++ host mirror (needletail.hpp) on the C ABI: the reference's tests re-stated in C++ (README loop on 28S.fasta)."""
+    import os, subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "test_host_mirror")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe,
+                           "-L", os.path.join(ROOT, "needletail_b200"), "-lntgpu", "-Wl,-rpath," + os.path.join(ROOT, "needletail_b200")])
+    fa = tmp_path / "28S.fasta"
+    fa.write_bytes(load_fixtures()["data/28S.fasta"])
+    out = subprocess.run([exe, str(fa)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "738580 bases" in out.stdout and "8108 AAAAs" in out.stdout
