@@ -14,7 +14,7 @@ import zlib
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libntgpu.so")
+_SO = os.environ.get("NTGPU_SO", os.path.join(_HERE, "libntgpu.so"))   # NTGPU_SO: experiment builds only
 
 # ntg_status (include/ntgpu.h) — 1..7 == needletail::errors::ParseErrorKind (src/errors.rs:28-43)
 OK = 0

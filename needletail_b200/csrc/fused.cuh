@@ -23,13 +23,13 @@
 #include "common.cuh"
 
 namespace fused {
-constexpr int NT = 192;                  // 6 warps; 3 CTAs per SM (112 registers per thread)
+constexpr int NT = 128;                  // 4 warps = one per SM sub-partition; 4 CTAs per SM (128 registers per thread)
 constexpr int ROWB = 256;                // P1 scans the tile in 256 B rows, one row per thread per round
 constexpr int ROWW = ROWB / 4;
-constexpr int TILE = 59 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
+constexpr int TILE = 40 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
 constexpr int MAXROUNDS = (TILE / ROWB + NT - 1) / NT;   // 2
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
-constexpr int NLMAX = 3072;              // newline capacity per tile (mean line >= 18.7 B)
+constexpr int NLMAX = 2560;              // newline capacity per tile (mean line >= 16 B)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
 constexpr int LONGMAX = TILE / SEG + 2;
 constexpr uint64_t NONE = ~0ull;
@@ -357,6 +357,47 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
     return true;
 }
 
+// =============================================================================== look-back
+__device__ __forceinline__ SState shfl_state(const SState& v, int src) {
+    SState r;
+    r.count = __shfl_sync(0xffffffffu, v.count, src);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.last[i] = __shfl_sync(0xffffffffu, v.last[i], src);
+    r.n_starts = __shfl_sync(0xffffffffu, v.n_starts, src);
+    r.hdr = __shfl_sync(0xffffffffu, v.hdr, src);
+    r.first_nl = __shfl_sync(0xffffffffu, v.first_nl, src);
+    return r;
+}
+// Exclusive prefix of tile t, computed by one whole warp: lane l inspects tile base-l, so 32 predecessors
+// are examined per step (a serial walk makes look-backs slow, which lengthens the window of tiles that have
+// only published aggregates, which makes look-backs slower still).
+__device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
+    SState suffix = identity_state();
+    int64_t base = (int64_t)t - 1;
+    for (;;) {
+        const int64_t j = base - (int64_t)lane;
+        uint32_t st = 2;                                            // before the first tile: inclusive(identity)
+        if (j >= 0) { const uint32_t f = ld_acquire_u32(&P.slots[j].flag); st = ((f >> 2) == epoch) ? (f & 3u) : 0u; }
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, st == 2), nr_mask = __ballot_sync(0xffffffffu, st == 0);
+        const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
+        const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
+        if (nr_mask & need) { __nanosleep(20); continue; }
+        const int top = first_inc < 32 ? first_inc : 31;
+        SState acc = identity_state();                              // lanes above `top` contribute the identity
+        if (j >= 0 && (int)lane <= top) acc = ((int)lane == first_inc) ? P.slots[j].inc : P.slots[j].agg;
+        // ordered tree reduction: lane l holds tile base-l, higher lanes are EARLIER tiles; combine() is associative
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const SState earlier = shfl_state(acc, (int)lane + d < 32 ? (int)lane + d : (int)lane);
+            if ((int)lane + d < 32) acc = combine(earlier, acc);
+        }
+        acc = shfl_state(acc, 0);
+        suffix = combine(acc, suffix);
+        if (first_inc < 32) return suffix;
+        base -= 32;
+    }
+}
+
 // =============================================================================== the kernel
 __device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
     // global position -> byte, from shared memory when resident, else from global memory
@@ -396,7 +437,7 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
 }
 
 template <int KW, bool MINI, int W, int FK, int FM>
-__global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
+__global__ void __launch_bounds__(NT, 4) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -508,8 +549,8 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             last_start1 = (uint32_t)S.bcast[0];
         }
 
-        // ---- P2c: publish aggregate, decoupled look-back, publish inclusive prefix (thread 0)
-        if (tid == 0) {
+        // ---- P2c: publish aggregate, decoupled look-back (warp 0, 32 predecessors per step), publish inclusive prefix
+        if (tid < 32) {
             SState agg = identity_state();
             agg.count = C;
             if (!overflow) for (uint32_t j = 0; j < 4 && j < C; j++) agg.last[j] = tile_start + S.nl[C - 1 - j];
@@ -519,27 +560,22 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                 if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
             }
             TileSlot* slot = &P.slots[t];
-            SState pre = identity_state();
-            if (t > 0) {
+            if (t > 0 && lane == 0) {
                 slot->agg = agg;
                 __threadfence();
                 st_release_u32(&slot->flag, epoch * 4 + 1);
-                SState accst = identity_state();
-                uint64_t j = t - 1;
-                for (;;) {
-                    const uint32_t f = ld_acquire_u32(&P.slots[j].flag);
-                    if ((f >> 2) != epoch || (f & 3) == 0) { __nanosleep(32); continue; }
-                    if ((f & 3) == 2) { pre = combine(P.slots[j].inc, accst); break; }
-                    accst = combine(P.slots[j].agg, accst);
-                    j--;                                                // tile 0 always publishes state 2
-                }
             }
-            const SState inc = combine(pre, agg);
-            slot->inc = inc;
-            __threadfence();
-            st_release_u32(&slot->flag, epoch * 4 + 2);
-            S.prefix = pre;
-            if (t + 1 == P.num_tiles) *P.final_state = inc;
+            __syncwarp();
+            SState pre = identity_state();
+            if (t > 0) pre = warp_lookback(P, t, epoch, lane);
+            if (lane == 0) {
+                const SState inc = combine(pre, agg);
+                slot->inc = inc;
+                __threadfence();
+                st_release_u32(&slot->flag, epoch * 4 + 2);
+                S.prefix = pre;
+                if (t + 1 == P.num_tiles) *P.final_state = inc;
+            }
         }
         if (tid == 0) S.n_long = 0;
         __syncthreads();
