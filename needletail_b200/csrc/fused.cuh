@@ -23,14 +23,16 @@
 #include "common.cuh"
 
 namespace fused {
-constexpr int NT = 128;                  // 4 warps = one per SM sub-partition; 4 CTAs per SM (128 registers per thread)
+constexpr int NT = 192;                  // 6 warps; 3 CTAs per SM (96 registers per thread) - measured best of 128x4 / 192x3
 constexpr int ROWB = 256;                // P1 scans the tile in 256 B rows, one row per thread per round
 constexpr int ROWW = ROWB / 4;
-constexpr int TILE = 40 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
+constexpr int TILE = 59 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
 constexpr int MAXROUNDS = (TILE / ROWB + NT - 1) / NT;   // 2
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
-constexpr int NLMAX = 2560;              // newline capacity per tile (mean line >= 16 B)
+constexpr int NLMAX = 3072;              // newline capacity per tile (mean line >= 19.7 B)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
+constexpr int CHUNK = 1;                 // tiles claimed per ticket. (>1 chains prefixes inside a CTA but serialises chunks:
+                                         // a chunk's first tile then waits for the LAST tile of the previous chunk - measured 3700x slower)
 constexpr int LONGMAX = TILE / SEG + 2;
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
@@ -136,6 +138,7 @@ struct __align__(16) Smem {
     uint32_t warp_tmp[NT / 32 + 2];
     uint64_t red[NT / 32][9];
     SState prefix;                     // exclusive prefix of this tile
+    SState last_inc;                   // inclusive prefix of the previous tile of this CTA's chunk
     uint32_t tile_idx;
     uint32_t n_long;
     uint32_t long_line[LONGMAX];       // line indices of long sequence lines
@@ -437,7 +440,7 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
 }
 
 template <int KW, bool MINI, int W, int FK, int FM>
-__global__ void __launch_bounds__(NT, 4) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
+__global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -455,11 +458,19 @@ __global__ void __launch_bounds__(NT, 4) k_fused(const Params P, const uint64_t 
     const uint8_t* sb = S.tile;
     const bool fasta = P.format == NTG_FMT_FASTA;
 
+    uint32_t in_chunk = CHUNK;                     // position inside the claimed chunk (CHUNK = claim a new one)
+    uint64_t chunk_first = 0;
     for (;;) {
-        if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint64_t t = tile_begin + S.tile_idx;
+        if (in_chunk == CHUNK) {
+            if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
+            __syncthreads();
+            chunk_first = tile_begin + (uint64_t)S.tile_idx * CHUNK;
+            in_chunk = 0;
+        } else __syncthreads();
+        const uint64_t t = chunk_first + in_chunk;
         if (t >= tile_end) break;
+        const bool chained = in_chunk > 0;           // prefix = inclusive prefix of the tile this CTA just finished
+        in_chunk++;
         const uint32_t TB = P.tile_bytes;
         const uint64_t tile_start = t * (uint64_t)TB;
         const uint32_t avail = (uint32_t)min((uint64_t)TB, P.n - tile_start);
@@ -560,20 +571,22 @@ __global__ void __launch_bounds__(NT, 4) k_fused(const Params P, const uint64_t 
                 if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
             }
             TileSlot* slot = &P.slots[t];
-            if (t > 0 && lane == 0) {
+            if (t > 0 && !chained && lane == 0) {
                 slot->agg = agg;
                 __threadfence();
                 st_release_u32(&slot->flag, epoch * 4 + 1);
             }
             __syncwarp();
             SState pre = identity_state();
-            if (t > 0) pre = warp_lookback(P, t, epoch, lane);
+            if (chained) pre = S.last_inc;
+            else if (t > 0) pre = warp_lookback(P, t, epoch, lane);
             if (lane == 0) {
                 const SState inc = combine(pre, agg);
                 slot->inc = inc;
                 __threadfence();
                 st_release_u32(&slot->flag, epoch * 4 + 2);
                 S.prefix = pre;
+                S.last_inc = inc;
                 if (t + 1 == P.num_tiles) *P.final_state = inc;
             }
         }

@@ -149,7 +149,7 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
 static int fused_launch(ntg_ctx* ctx, uint64_t tb, uint64_t te, int li) {
     FusedState* st = ctx->fused;
     if (te <= tb) return NTG_OK;
-    uint64_t nt = te - tb;
+    uint64_t nt = (te - tb + fused::CHUNK - 1) / fused::CHUNK;        // CTAs claim chunks of CHUNK consecutive tiles
     unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
     fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m, st->P.has_query != 0);
     kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
