@@ -197,7 +197,8 @@ typedef struct ntg_tallies {
     uint64_t n_minimizers;     /* bit_kmers(k,false) items                               */
     uint64_t minimizer_sum;    /* wrapping sum of bitkmer::minimizer(kmer, m).0          */
     uint64_t reserved[7];      /* reserved[0]: 0 = single-pass fused kernel produced these; else bitmask of why the exact
-                                  record-table path re-ran (1 parse error, 2 newline-dense tile, 4 whitespace run > halo) */
+                                  record-table path re-ran (1 parse error, 2 newline-dense tile, 4 whitespace run > halo);
+                                  reserved[1]: non-zero when the warp-specialised short-read kernel handed over to the general kernel */
 } ntg_tallies;
 
 /* host bytes: H2D copies are pipelined with the kernel inside the call (the end-to-end path) */

@@ -334,6 +334,9 @@ class Context:
         d["err_kind"] = ERROR_KINDS.get(e.kind) if e.kind else None
         d["err_line"] = int(e.line)
         d["fallback"] = int(t.reserved[0])      # 0: the single-pass fused kernel produced the tallies
+        d["ws_handover"] = int(t.reserved[1])   # != 0: the warp-specialised kernel handed over to the general fused kernel
+        d["ws_cycles"] = {"claim": int(t.reserved[2]), "scan": int(t.reserved[3]), "lookback_retry": int(t.reserved[4]),
+                          "walker_wait": int(t.reserved[5]), "walker_work": int(t.reserved[6])}
         return d
 
     def tally(self, data, k, m=0, iupac=False, query=None):

@@ -37,7 +37,7 @@ constexpr int LONGMAX = TILE / SEG + 2;
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
 
-enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4 };
+enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4, FLAG_WS_BAIL = 8 };
 
 // carried scan state (prefix over tiles)
 struct SState {
@@ -114,6 +114,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -374,7 +380,10 @@ __device__ __forceinline__ SState shfl_state(const SState& v, int src) {
 // Exclusive prefix of tile t, computed by one whole warp: lane l inspects tile base-l, so 32 predecessors
 // are examined per step (a serial walk makes look-backs slow, which lengthens the window of tiles that have
 // only published aggregates, which makes look-backs slower still).
-__device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
+// BLOCKING = false: returns false (result undefined) instead of waiting when a needed predecessor has not
+// published yet, so that a producer warp can do other work and retry.
+template <bool BLOCKING = true>
+__device__ __forceinline__ bool warp_lookback_try(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, SState& out) {
     SState suffix = identity_state();
     int64_t base = (int64_t)t - 1;
     for (;;) {
@@ -384,7 +393,7 @@ __device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uin
         const uint32_t inc_mask = __ballot_sync(0xffffffffu, st == 2), nr_mask = __ballot_sync(0xffffffffu, st == 0);
         const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
         const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if (nr_mask & need) { __nanosleep(20); continue; }
+        if (nr_mask & need) { if (!BLOCKING) return false; __nanosleep(20); continue; }
         const int top = first_inc < 32 ? first_inc : 31;
         SState acc = identity_state();                              // lanes above `top` contribute the identity
         if (j >= 0 && (int)lane <= top) acc = ((int)lane == first_inc) ? P.slots[j].inc : P.slots[j].agg;
@@ -396,9 +405,14 @@ __device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uin
         }
         acc = shfl_state(acc, 0);
         suffix = combine(acc, suffix);
-        if (first_inc < 32) return suffix;
+        if (first_inc < 32) { out = suffix; return true; }
         base -= 32;
     }
+}
+__device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
+    SState r;
+    warp_lookback_try<true>(P, t, epoch, lane, r);
+    return r;
 }
 
 // =============================================================================== the kernel

@@ -1,6 +1,7 @@
 // fused_host.cuh — host orchestration of the fused tallies path.  Part of the unity build.
 #pragma once
 #include "fused.cuh"
+#include "fused_ws.cuh"
 #include "parse.cuh"
 
 struct FusedControl {           // device-resident control block, zeroed per call
@@ -26,6 +27,9 @@ struct FusedState {
     cudaEvent_t ev_chunk[FUSED_MAX_LAUNCHES] = {};
     uint8_t* feed_buf = nullptr; size_t feed_cap = 0;   // device staging for host feeds
     const uint8_t* host_bytes = nullptr;                // when the call was fed from host memory
+    bool used_ws = false;                               // the pending call ran the warp-specialised kernel
+    uint32_t general_tile_bytes = 0;                    // tile size for a re-run with the general kernel
+    int max_ctas_ws = 0;
 };
 
 typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
@@ -47,6 +51,15 @@ static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) 
     if (m == 0) return k_fused<1, false, 0, 0, 0>;
     if (k - m + 1 == 11) return k_fused<1, true, 11, 0, 0>;
     return k_fused<1, true, 0, 0, 0>;
+}
+
+// warp-specialised kernel: FASTQ, constant-folded shapes, no query
+static fused_kernel_t pick_ws_kernel(uint32_t k, uint32_t m, bool has_query, int format) {
+    if (format != NTG_FMT_FASTQ || has_query) return nullptr;
+    if (k == 31 && m == 21) return fused_ws::k_fused_ws<31, 21>;
+    if (k == 21 && m == 11) return fused_ws::k_fused_ws<21, 11>;
+    if (k == 31 && m == 0) return fused_ws::k_fused_ws<31, 0>;
+    return nullptr;
 }
 
 static int fused_init(ntg_ctx* ctx) {
@@ -72,6 +85,16 @@ static int fused_init(ntg_ctx* ctx) {
         occ_min = occ < occ_min ? occ : occ_min;
     }
     st->max_ctas = occ_min * ctx->sm_count;     // persistent grid: every CTA resident (look-back needs forward progress)
+    fused_kernel_t wks[3] = {fused_ws::k_fused_ws<31, 21>, fused_ws::k_fused_ws<21, 11>, fused_ws::k_fused_ws<31, 0>};
+    int occ_ws = 1 << 30;
+    for (auto kf : wks) {
+        NTG_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fused_ws::SmemWS)));
+        int occ = 0;
+        NTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, fused_ws::WNT, sizeof(fused_ws::SmemWS)));
+        if (occ < 1) return ntg_set_error(ctx, NTG_ECUDA, "warp-specialised kernel does not fit on an SM");
+        occ_ws = occ < occ_ws ? occ : occ_ws;
+    }
+    st->max_ctas_ws = occ_ws * ctx->sm_count;
     return NTG_OK;
 }
 static void fused_destroy(ntg_ctx* ctx) {
@@ -117,10 +140,14 @@ static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
     return tb;
 }
 
-static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes) {
+static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes,
+                       bool allow_ws = true) {
     NTG_TRY(fused_init(ctx));
     FusedState* st = ctx->fused;
     if (st->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is already pending: collect it first");
+    st->general_tile_bytes = tile_bytes;
+    st->used_ws = allow_ws && pick_ws_kernel(cfg->k, cfg->m, cfg->has_query != 0, format) != nullptr && getenv("NTGPU_WS") != nullptr;   // opt-in experiment
+    if (st->used_ws) tile_bytes = fused_ws::TB;
     if ((reinterpret_cast<uintptr_t>(dbytes) & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
     if (num_tiles > st->slots_cap) {
@@ -150,6 +177,14 @@ static int fused_launch(ntg_ctx* ctx, uint64_t tb, uint64_t te, int li) {
     FusedState* st = ctx->fused;
     if (te <= tb) return NTG_OK;
     uint64_t nt = (te - tb + fused::CHUNK - 1) / fused::CHUNK;        // CTAs claim chunks of CHUNK consecutive tiles
+    if (st->used_ws) {
+        unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas_ws ? nt : (uint64_t)st->max_ctas_ws);
+        fused_kernel_t kf = pick_ws_kernel(st->P.k, st->P.m, st->P.has_query != 0, st->P.format);
+        kf<<<grid, fused_ws::WNT, sizeof(fused_ws::SmemWS), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
+        ctx->launches++;
+        NTG_CUDA(ctx, cudaGetLastError());
+        return NTG_OK;
+    }
     unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
     fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m, st->P.has_query != 0);
     kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
@@ -175,6 +210,8 @@ static void tallies_from_ctrl(const FusedControl* c, ntg_tallies* out) {
     out->n_records = c->tallies[0]; out->n_bases = c->tallies[1]; out->n_kmers = c->tallies[2]; out->n_not_rc = c->tallies[3];
     out->kmer_sum_lo = c->tallies[4]; out->kmer_sum_hi = c->tallies[5]; out->n_query = c->tallies[6];
     out->n_minimizers = c->tallies[7]; out->minimizer_sum = c->tallies[8];
+    for (int i = 0; i < 5; i++) out->reserved[2 + i] = c->tallies[9 + i];   // producer cycle accounting of the warp-specialised kernel
+    out->reserved[5] = c->tallies[14]; out->reserved[6] = c->tallies[15];   // (walker wait / work cycles replace two of them)
 }
 
 static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, float* fused_kernel_ms) {
@@ -185,8 +222,21 @@ static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, f
     if (fused_kernel_ms) NTG_CUDA(ctx, cudaEventElapsedTime(fused_kernel_ms, st->ev_k0, st->ev_k1));
     if (err) std::memset(err, 0, sizeof(*err));
     if (err) err->format = st->P.format;
-    const uint32_t fast_flags = st->h_ctrl->flags;
+    uint32_t fast_flags = st->h_ctrl->flags;
     if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
+    const uint32_t ws_flags = st->used_ws ? fast_flags : 0;
+    if (st->used_ws && (fast_flags & fused::FLAG_WS_BAIL)) {
+        // the warp-specialised kernel met something outside its remit: one pass of the general kernel over the same bytes
+        const ntg_tally_config cfg = st->cfg;
+        NTG_TRY(fused_begin(ctx, st->P.bytes, st->P.n, st->P.format, &cfg, st->general_tile_bytes, /*allow_ws=*/false));
+        int s2 = fused_launch(ctx, 0, st->P.num_tiles, 0);
+        if (s2 == NTG_OK) s2 = fused_finish_enqueue(ctx);
+        st->pending = false;
+        NTG_TRY(s2);
+        NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        fast_flags = st->h_ctrl->flags;
+        if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); out->reserved[1] = ws_flags; return NTG_OK; }
+    }
 
     // ---- exact fallback: record table on the device, then one thread per delivered record
     ntg_records* recs = nullptr;
@@ -208,6 +258,7 @@ static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, f
     ntg_records_free(recs);
     if (e) return ntg_set_error(ctx, NTG_ECUDA, "fallback: %s", cudaGetErrorString(e));
     tallies_from_ctrl(st->h_ctrl, out);
+    out->reserved[1] = ws_flags;
     out->reserved[0] = fast_flags;          // why the exact path ran: 1 parse error, 2 newline-dense tile, 4 whitespace run > halo
     return NTG_OK;
 }

@@ -3,6 +3,7 @@
 //        (see needletail_b200/build.py).  No torch, no CPU compute fallback: without a CUDA device
 //        ntg_create fails and every entry point needs a context.
 #include <cstdarg>
+#include <cstdlib>
 #include <dlfcn.h>
 
 #include "common.cuh"
@@ -312,7 +313,8 @@ int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tall
     st->host_bytes = bytes;
     // chunk size: a multiple of the tile, at most FUSED_MAX_LAUNCHES chunks
     const uint64_t num_tiles = st->P.num_tiles;
-    uint64_t tiles_per_chunk = ((size_t(256) << 20) + tile_bytes - 1) / tile_bytes;
+    const uint32_t tbytes = st->P.tile_bytes;             // (the warp-specialised kernel has its own tile size)
+    uint64_t tiles_per_chunk = ((size_t(256) << 20) + tbytes - 1) / tbytes;
     if ((num_tiles + tiles_per_chunk - 1) / tiles_per_chunk > FUSED_MAX_LAUNCHES)
         tiles_per_chunk = (num_tiles + FUSED_MAX_LAUNCHES - 1) / FUSED_MAX_LAUNCHES;
     // the copy stream must not overwrite feed_buf while an earlier call's kernels still read it, and the
@@ -325,7 +327,7 @@ int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tall
     int li = 0;
     for (uint64_t tb = 0; tb < num_tiles && !e && s == NTG_OK; tb += tiles_per_chunk, li++) {
         const uint64_t te = tb + tiles_per_chunk < num_tiles ? tb + tiles_per_chunk : num_tiles;
-        const size_t b0 = tb * (uint64_t)tile_bytes, b1 = te * (uint64_t)tile_bytes < n ? te * (uint64_t)tile_bytes : n;
+        const size_t b0 = tb * (uint64_t)tbytes, b1 = te * (uint64_t)tbytes < n ? te * (uint64_t)tbytes : n;
         e = cudaMemcpyAsync(st->feed_buf + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream);
         if (!e) e = cudaEventRecord(st->ev_chunk[li], ctx->copy_stream);
         if (!e) e = cudaStreamWaitEvent(ctx->stream, st->ev_chunk[li], 0);
