@@ -23,13 +23,14 @@
 #include "common.cuh"
 
 namespace fused {
-constexpr int NT = 192;                  // 6 warps; 3 CTAs per SM (96 registers per thread) - measured best of 128x4 / 192x3
+constexpr int NTW = 288;                 // 9 walker warps ...
+constexpr int NT = NTW + 32;             // ... + 1 coordinator warp (highest warp id); 2 CTAs per SM, 96 registers per thread
 constexpr int ROWB = 256;                // P1 scans the tile in 256 B rows, one row per thread per round
 constexpr int ROWW = ROWB / 4;
-constexpr int TILE = 59 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
-constexpr int MAXROUNDS = (TILE / ROWB + NT - 1) / NT;   // 2
+constexpr int TILE = 84 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
+constexpr int MAXROUNDS = (TILE / ROWB + NTW - 1) / NTW;   // 2  (rows are scanned by the walker threads)
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
-constexpr int NLMAX = 3072;              // newline capacity per tile (mean line >= 19.7 B)
+constexpr int NLMAX = 2048;              // newline capacity per tile (mean line >= 42 B at full tile size)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
 constexpr int CHUNK = 1;                 // tiles claimed per ticket. (>1 chains prefixes inside a CTA but serialises chunks:
                                          // a chunk's first tile then waits for the LAST tile of the previous chunk - measured 3700x slower)
@@ -37,7 +38,7 @@ constexpr int LONGMAX = TILE / SEG + 2;
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
 
-enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4, FLAG_WS_BAIL = 8 };
+enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4, FLAG_WS_BAIL = 8, FLAG_SPEC_MISS = 16 };
 
 // carried scan state (prefix over tiles)
 struct SState {
@@ -90,6 +91,8 @@ struct Params {
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
     int has_query;
     uint32_t one;                      // == 1 (run-time constant for mad.wide)
+    uint32_t spec;                     // FASTQ: walkers start on a locally inferred line phase while the coordinator warp
+                                       // does the look-back; a wrong guess raises FLAG_SPEC_MISS and the host re-runs with spec = 0
     uint64_t q_lo, q_hi;
 };
 
@@ -136,8 +139,8 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 struct __align__(16) Smem {
     uint8_t halo[HALO];
     uint8_t tile[TILE];
-    uint16_t nl[NLMAX + 8];            // sorted tile-relative newline offsets
-    uint16_t rstart[NLMAX + 8];        // FASTA: per line, tile-relative (+HALO) start of its sequence region
+    uint32_t nl[NLMAX + 8];            // sorted tile-relative newline offsets
+    uint32_t rstart[NLMAX + 8];        // FASTA: per line, tile-relative (+HALO) start of its sequence region
     uint8_t lut[256];                  // 0..3 ACGT, 4 kept non-ACGT, 0x85 deleted (space/tab), 0x86 deleted (\r \n)
     uint32_t rins[256];                // fast walker: complement base pre-shifted into the high word of R
     uint64_t bar;
@@ -145,6 +148,7 @@ struct __align__(16) Smem {
     uint64_t red[NT / 32][9];
     SState prefix;                     // exclusive prefix of this tile
     SState last_inc;                   // inclusive prefix of the previous tile of this CTA's chunk
+    volatile uint32_t prefix_seq;      // number of tiles of this CTA whose prefix has been resolved by the coordinator
     uint32_t tile_idx;
     uint32_t n_long;
     uint32_t long_line[LONGMAX];       // line indices of long sequence lines
@@ -453,8 +457,34 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
     }
 }
 
+// FASTQ line phase inferred from the tile alone: which p makes role(i) = (p + i) & 3 consistent with the first bytes
+// of the first lines that start in this tile ('@' at role 0, '+' at role 2)?  Returns 0..3, or 4 when fewer than four
+// line starts are visible or the evidence is not unique.  Used only to START early; the true phase (newline ordinal
+// from the look-back) is checked afterwards and a mismatch raises FLAG_SPEC_MISS.
+template <typename NLT>
+__device__ __forceinline__ uint32_t guess_phase(const NLT* __restrict__ nl, const uint8_t* __restrict__ sb, uint32_t Cs,
+                                                uint32_t avail, bool line0_starts_here) {
+    uint32_t ok = 0xF, seen = 0;
+    for (uint32_t i = line0_starts_here ? 0u : 1u; i <= Cs && seen < 8; i++, seen++) {
+        const uint32_t s = i ? (uint32_t)nl[i - 1] + 1u : 0u;
+        if (s >= avail) break;
+        const uint8_t c = sb[s];
+        ok &= ~((c != '@' ? 1u : 0u) << ((0u - i) & 3u));
+        ok &= ~((c != '+' ? 1u : 0u) << ((2u - i) & 3u));
+    }
+    if (seen < 4 || __popc(ok) != 1) return 4;
+    return (uint32_t)__ffs((int)ok) - 1u;
+}
+// start of the line that continues into the tile, found in the back halo (tile-relative, < 0); exact when a newline is
+// visible, else the halo limit
+__device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, uint32_t halo, int& lo, bool& lo_exact) {
+    for (int p = -1; p >= -(int)halo; p--)
+        if (sb[p] == '\n') { lo = p + 1; lo_exact = true; return; }
+    lo = -(int)halo; lo_exact = false;
+}
+
 template <int KW, bool MINI, int W, int FK, int FM>
-__global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
+__global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -467,10 +497,13 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
     }
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
     __syncthreads();
-    uint32_t parity = 0, slow = 0;
+    uint32_t parity = 0, slow = 0, my_seq = 0;
     Acc acc;
     const uint8_t* sb = S.tile;
     const bool fasta = P.format == NTG_FMT_FASTA;
+    const bool is_coord = tid >= NTW;                 // the coordinator warp: look-back, line events (FASTQ)
+    const bool spec = P.spec != 0 && !fasta;          // walkers start on an inferred phase, the coordinator verifies it
+    if (tid == 0) S.prefix_seq = 0;
 
     uint32_t in_chunk = CHUNK;                     // position inside the claimed chunk (CHUNK = claim a new one)
     uint64_t chunk_first = 0;
@@ -491,6 +524,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
         const uint32_t halo = t > 0 ? HALO : 0;
         const uint32_t bulk = avail & ~15u;
 
+        if (tid == 0) S.n_long = 0;
         // ---- P0: stage the tile (+ back halo) with one bulk async copy
         if (tid == 0 && halo + bulk) {
             mbar_expect_tx(&S.bar, halo + bulk);
@@ -508,8 +542,8 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
 #pragma unroll
         for (int rd = 0; rd < MAXROUNDS; rd++) {
             cnt[rd] = 0; wmask[rd] = 0;
-            const uint32_t rowi = rd * NT + tid;
-            if (rowi < nrows) {
+            const uint32_t rowi = rd * NTW + tid;
+            if (tid < NTW && rowi < nrows) {
                 const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW;
 #pragma unroll 8
                 for (int j = 0; j < ROWW; j++) {
@@ -535,7 +569,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
 #pragma unroll
             for (int rd = 0; rd < MAXROUNDS; rd++) {
                 if (!cnt[rd]) continue;
-                const uint32_t rowi = rd * NT + tid;
+                const uint32_t rowi = rd * NTW + tid;
                 const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW;
                 uint32_t o = rd == 0 ? (offp & 0xFFFFu) : C0 + (offp >> 16);
                 uint64_t mk = wmask[rd];
@@ -545,7 +579,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                     const uint32_t wv = row[jj];
 #pragma unroll
                     for (int bsel = 0; bsel < 4; bsel++)
-                        if (((wv >> (8 * bsel)) & 0xFF) == '\n') S.nl[o++] = (uint16_t)(rowi * ROWB + jj * 4 + bsel);
+                        if (((wv >> (8 * bsel)) & 0xFF) == '\n') S.nl[o++] = (uint32_t)(rowi * ROWB + jj * 4 + bsel);
                 }
             }
         }
@@ -574,8 +608,9 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             last_start1 = (uint32_t)S.bcast[0];
         }
 
-        // ---- P2c: publish aggregate, decoupled look-back (warp 0, 32 predecessors per step), publish inclusive prefix
-        if (tid < 32) {
+        // ---- P2c: publish aggregate, decoupled look-back (coordinator warp, 32 predecessors per step), publish inclusive prefix
+        SState pre = identity_state();
+        if (is_coord) {
             SState agg = identity_state();
             agg.count = C;
             if (!overflow) for (uint32_t j = 0; j < 4 && j < C; j++) agg.last[j] = tile_start + S.nl[C - 1 - j];
@@ -591,7 +626,6 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                 st_release_u32(&slot->flag, epoch * 4 + 1);
             }
             __syncwarp();
-            SState pre = identity_state();
             if (chained) pre = S.last_inc;
             else if (t > 0) pre = warp_lookback(P, t, epoch, lane);
             if (lane == 0) {
@@ -602,11 +636,13 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                 S.prefix = pre;
                 S.last_inc = inc;
                 if (t + 1 == P.num_tiles) *P.final_state = inc;
+                __threadfence_block();
+                S.prefix_seq = my_seq + 1;
             }
+            __syncwarp();
         }
-        if (tid == 0) S.n_long = 0;
-        __syncthreads();
-        const SState pre = S.prefix;
+        bool have_pre = is_coord;
+        if (!spec) { __syncthreads(); pre = S.prefix; have_pre = true; }      // everyone needs the prefix before going on
         // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
         auto prev_nl = [&](uint32_t i, uint32_t back) -> uint64_t {
             if (i >= back) return tile_start + S.nl[i - back];
@@ -620,6 +656,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
         // warm-up bound of a fragment of line i: the line start (FASTQ) / the sequence-region start (FASTA)
         auto fastq_bound = [&](uint32_t i, int a, int& lo, bool& lo_exact) {
             if (i > 0 || line0_starts_here) { lo = line_start_rel(i); lo_exact = true; (void)a; }
+            else if (!have_pre) halo_line_start(sb, halo, lo, lo_exact);
             else {
                 const uint64_t p1 = pre.last[0];
                 const int64_t ls = (p1 == NONE ? 0 : (int64_t)p1 + 1) - (int64_t)tile_start;
@@ -640,13 +677,23 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
 
         if (!fasta) {
             // ---------------------------------------------------------------------------- FASTQ
-            const uint32_t ord0 = (uint32_t)(pre.count & 3);
-            // (A) every line: start bytes, n_bases, record completion  (cheap, all lanes busy)
-            for (uint32_t i = tid; i <= Cs; i += NT) {
+            uint32_t ord0;
+            const uint32_t guess = spec ? guess_phase(S.nl, sb, Cs, avail, line0_starts_here) : 4u;
+            if (have_pre) ord0 = (uint32_t)(pre.count & 3);
+            else if (guess != 4) ord0 = guess;
+            else {                                                      // no unique local evidence: wait for the coordinator
+                while (S.prefix_seq <= my_seq) __nanosleep(32);
+                __threadfence_block();
+                pre = S.prefix; have_pre = true;
+                ord0 = (uint32_t)(pre.count & 3);
+            }
+            if (spec && is_coord && guess != 4 && guess != ord0) slow |= FLAG_SPEC_MISS;
+            // (A) line events: start bytes, n_bases, record completion (fastq.rs:240-285).
+            auto line_events = [&](uint32_t i) {
                 const uint32_t role = (ord0 + i) & 3;                     // 0 header, 1 sequence, 2 separator, 3 quality
                 const int s = line_start_rel(i);
                 const bool starts = (i > 0 || line0_starts_here) && (uint32_t)s < avail;
-                if (starts) {                                             // validate(): fastq.rs:240-263
+                if (starts) {
                     if (role == 0 && sb[s] != '@') slow |= FLAG_PARSE_ERROR;
                     if (role == 2 && sb[s] != '+') slow |= FLAG_PARSE_ERROR;
                 }
@@ -662,21 +709,32 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
                         else {
                             const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
                             const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
-                            if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;                   // fastq.rs:276-284
+                            if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;
                             acc.n_records++;
                         }
                     }
                 }
-            }
-            // (B) sequence lines only: thread j walks the j-th role-1 line of the tile (every 4th line)
+            };
+            // Without speculation every thread has the prefix and takes lines tid, tid+NT, ...  With speculation the
+            // coordinator warp (which has the prefix) takes the lines that may need it — the first four of the tile —
+            // and each walker takes the lines >= 4 of "its" record, whose previous newlines are all in the tile's list.
+            if (!spec) { for (uint32_t i = tid; i <= Cs; i += NT) line_events(i); }
+            else if (is_coord) { for (uint32_t i = lane; i <= Cs && i < 4; i += 32) line_events(i); }
+            // (B) sequence lines only: walker thread j takes the j-th role-1 line of the tile (every 4th line)
             const uint32_t i_first = (1u - ord0) & 3u;
-            for (uint32_t i = i_first + 4u * tid; i <= Cs; i += 4u * NT) {
-                const int a = line_start_rel(i), b = line_end_rel(i);
-                if (b <= a) continue;
-                if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
-                int lo; bool lo_exact;
-                fastq_bound(i, a, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, false, slow);
+            if (!is_coord) {
+                for (uint32_t i = i_first + 4u * tid; i <= Cs + 1; i += 4u * NTW) {
+                    if (spec) {                                             // events of this record's lines (header .. quality)
+                        for (uint32_t e = (i ? i - 1 : 0); e <= i + 2 && e <= Cs; e++) if (e >= 4) line_events(e);
+                    }
+                    if (i > Cs) continue;
+                    const int a = line_start_rel(i), b = line_end_rel(i);
+                    if (b <= a) continue;
+                    if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
+                    int lo; bool lo_exact;
+                    fastq_bound(i, a, lo, lo_exact);
+                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, false, slow);
+                }
             }
         } else {
             // ---------------------------------------------------------------------------- FASTA
@@ -699,7 +757,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             __syncthreads();
             if (lane == 0 && tid > 0) run = s_prev[(tid >> 5) - 1];
             for (uint32_t i = i0; i < i1; i++) {
-                S.rstart[i] = (uint16_t)run;
+                S.rstart[i] = run;
                 if (i < Cs && is_header(i)) run = max(run, (uint32_t)S.nl[i] + 1 + HALO);
             }
             __syncthreads();
@@ -740,6 +798,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused(const Params P, const uint64_t 
             }
         }
         __syncthreads();
+        my_seq++;
     }
 
     // ---- P4: block reduction of the register tallies, 9 atomics per CTA

@@ -84,6 +84,7 @@ static int fused_init(ntg_ctx* ctx) {
         if (occ < 1) return ntg_set_error(ctx, NTG_ECUDA, "fused kernel does not fit on an SM");
         occ_min = occ < occ_min ? occ : occ_min;
     }
+    if (getenv("NTGPU_DEBUG")) fprintf(stderr, "[ntgpu] fused kernel occupancy: %d CTAs/SM\n", occ_min);
     st->max_ctas = occ_min * ctx->sm_count;     // persistent grid: every CTA resident (look-back needs forward progress)
     fused_kernel_t wks[3] = {fused_ws::k_fused_ws<31, 21>, fused_ws::k_fused_ws<21, 11>, fused_ws::k_fused_ws<31, 0>};
     int occ_ws = 1 << 30;
@@ -133,7 +134,7 @@ static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
         seqline_period = (double)ns / (double)seql;
         if ((double)ns / (double)nl > fused::SEG) return fused::TILE;
     }
-    double want = 0.97 * fused::NT * seqline_period;
+    double want = 0.97 * (format == NTG_FMT_FASTQ ? fused::NTW : fused::NT) * seqline_period;   // FASTQ: the coordinator warp does not walk
     uint32_t tb = (uint32_t)(want / 256.0) * 256u;
     if (tb < 16384u) tb = 16384u;
     if (tb > (uint32_t)fused::TILE) tb = fused::TILE;
@@ -162,6 +163,7 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
     P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.ticket = nullptr;
     P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
+    P.spec = (allow_ws && format == NTG_FMT_FASTQ && getenv("NTGPU_NO_SPEC") == nullptr) ? 1 : 0;
     P.q_lo = P.q_hi = 0;
     if (cfg->has_query)
         for (uint32_t i = 0; i < cfg->k; i++) {
@@ -224,9 +226,10 @@ static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, f
     if (err) err->format = st->P.format;
     uint32_t fast_flags = st->h_ctrl->flags;
     if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
-    const uint32_t ws_flags = st->used_ws ? fast_flags : 0;
-    if (st->used_ws && (fast_flags & fused::FLAG_WS_BAIL)) {
-        // the warp-specialised kernel met something outside its remit: one pass of the general kernel over the same bytes
+    const uint32_t ws_flags = (st->used_ws || (fast_flags & fused::FLAG_SPEC_MISS)) ? fast_flags : 0;
+    if ((st->used_ws && (fast_flags & fused::FLAG_WS_BAIL)) || (fast_flags & fused::FLAG_SPEC_MISS)) {
+        // the warp-specialised kernel met something outside its remit, or a speculated FASTQ line phase was wrong:
+        // one plain pass (no speculation) of the general kernel over the same bytes
         const ntg_tally_config cfg = st->cfg;
         NTG_TRY(fused_begin(ctx, st->P.bytes, st->P.n, st->P.format, &cfg, st->general_tile_bytes, /*allow_ws=*/false));
         int s2 = fused_launch(ctx, 0, st->P.num_tiles, 0);

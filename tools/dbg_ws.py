@@ -2,6 +2,8 @@ import sys, os
 sys.path.insert(0, os.getcwd())
 import needletail_b200 as nt
 ctx = nt.Context(0)
+import ctypes
+
 for nrec in (5000, 20000000):
     L=150; nb = nrec*(2*L+16)
     d = ctx.device_alloc(nb); ctx.synth_fastq_device(d, 0x5EED0002, 0, nrec, L, 0)
