@@ -229,9 +229,10 @@ def run_ours(args):
     achieved = nbytes / (kavg * 1e-3) / 1e9
     ratio = load_traffic_ratio()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ratio * nbytes) if ratio else None, "kernel": "fused::k_fused<1,true,11>", "kernel_ms": kavg,
+                "traffic": (ratio * nbytes) if ratio else None, "kernel": "fused::k_fused<1,true,11,31,21>", "kernel_ms": kavg,
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
-                "note": "integer-issue bound (see DESIGN.md): ~40 INT ops per base on the 64-lane ALU pipe"}
+                "traffic_note": "DRAM bytes per launch = ncu dram read+write bytes per input byte (profiles/traffic.json) x algorithmic bytes",
+                "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-issue bound, not HBM bound: ~65 SASS instructions per base, INT pipe 52% / issue slots 67% busy (profiles/r1d_*); see DESIGN.md"}
 
     # ---- end to end through the host-facing C-ABI call: pinned host FASTQ -> H2D -> fused kernel -> tallies
     e2e = None

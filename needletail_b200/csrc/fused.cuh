@@ -128,6 +128,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
@@ -150,6 +153,7 @@ struct __align__(16) Smem {
     SState last_inc;                   // inclusive prefix of the previous tile of this CTA's chunk
     volatile uint32_t prefix_seq;      // number of tiles of this CTA whose prefix has been resolved by the coordinator
     uint32_t tile_idx;
+    uint32_t tile_idx_next;            // ticket of the next tile, claimed by the coordinator during this one
     uint32_t n_long;
     uint32_t long_line[LONGMAX];       // line indices of long sequence lines
     uint32_t long_pref[LONGMAX + 1];   // exclusive prefix of piece counts
@@ -508,12 +512,11 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
     uint32_t in_chunk = CHUNK;                     // position inside the claimed chunk (CHUNK = claim a new one)
     uint64_t chunk_first = 0;
     for (;;) {
-        if (in_chunk == CHUNK) {
-            if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
-            __syncthreads();
-            chunk_first = tile_begin + (uint64_t)S.tile_idx * CHUNK;
-            in_chunk = 0;
-        } else __syncthreads();
+        // Static round-robin tile assignment: CTA b takes tiles b, b + grid, b + 2 grid, ...  (No ticket: a tile that is
+        // claimed early but processed late publishes its aggregate late and stalls every look-back behind it; with the
+        // static order the next tile is known in advance, so it can be prefetched into L2 without being "claimed".)
+        chunk_first = tile_begin + (uint64_t)blockIdx.x + (uint64_t)my_seq * gridDim.x;
+        in_chunk = 0;
         const uint64_t t = chunk_first + in_chunk;
         if (t >= tile_end) break;
         const bool chained = in_chunk > 0;           // prefix = inclusive prefix of the tile this CTA just finished
@@ -638,6 +641,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (t + 1 == P.num_tiles) *P.final_state = inc;
                 __threadfence_block();
                 S.prefix_seq = my_seq + 1;
+                // next tile of this CTA: pull it into L2 while the walkers work on this one
+                const uint64_t tn = t + gridDim.x;
+                if (tn < tile_end) {
+                    const uint64_t ns = tn * (uint64_t)TB;
+                    const uint32_t nbytes = (uint32_t)min((uint64_t)TB, P.n - ns) & ~15u;
+                    if (nbytes) bulk_prefetch_l2(P.bytes + ns, nbytes);
+                }
             }
             __syncwarp();
         }
