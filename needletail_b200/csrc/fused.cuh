@@ -784,13 +784,15 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         __syncthreads();
         // ---- long lines: SEG-byte pieces shared by the whole CTA
         const uint32_t n_long = min(S.n_long, (uint32_t)LONGMAX);
+        // piece length: about one piece per thread when the tile is made of long lines (at least 128 B, at most SEG)
+        const int PSEG = max(128, min(SEG, (int)(((avail + NT - 1) / NT + 15) & ~15u)));
         if (n_long) {
             if (tid == 0) {
                 // (order of long_line[] is arbitrary: atomics) -> prefix of piece counts
                 uint32_t sacc = 0;
                 for (uint32_t j = 0; j < n_long; j++) {
                     const uint32_t i = S.long_line[j];
-                    S.long_pref[j] = sacc; sacc += (uint32_t)(line_end_rel(i) - line_start_rel(i) + SEG - 1) / SEG;
+                    S.long_pref[j] = sacc; sacc += (uint32_t)(line_end_rel(i) - line_start_rel(i) + PSEG - 1) / PSEG;
                 }
                 S.long_pref[n_long] = sacc;
             }
@@ -801,7 +803,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 while (j + 1 < n_long && S.long_pref[j + 1] <= pc) j++;
                 const uint32_t i = S.long_line[j];
                 const int la = line_start_rel(i), lb = line_end_rel(i);
-                const int a = la + (int)(pc - S.long_pref[j]) * SEG, b = min(a + SEG, lb);
+                const int a = la + (int)(pc - S.long_pref[j]) * PSEG, b = min(a + PSEG, lb);
                 int lo; bool lo_exact;
                 if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
                 run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, fasta, slow);
