@@ -285,8 +285,8 @@ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8
 //  - F / R are kept as explicit 32-bit word pairs (low-aligned, < 2^62);
 //  - every 64-bit "a < b" is ONE DSETP on the otherwise idle FP64 pipe: two non-negative integers
 //    below 2^62 order exactly like the doubles with the same bit patterns (finite, positive);
-//  - sums are carried as separate 64-bit sums of the low / high 32-bit words (IMAD.WIDE on the FMA
-//    pipe, no carry chains) and folded when the item ends;
+//  - checksums are carried per item as a 64-bit sum of the low words and a 32-bit sum of the high words
+//    (3 integer adds per value) and folded when the item ends;
 //  - non-ACGT bases never branch: they only push `next_ok`, the first index where a k-mer may end.
 struct FastLuts {
     const uint8_t* cls;      // 0..3 code, 4 = kept non-ACGT, >= 0x80 = deleted byte
@@ -294,8 +294,6 @@ struct FastLuts {
     uint32_t one;            // 1, as a run-time value (keeps mad.wide from being strength-reduced to IADD3 pairs)
 };
 __device__ __forceinline__ bool lt62(uint64_t a, uint64_t b) { return __longlong_as_double((long long)a) < __longlong_as_double((long long)b); }
-// exact double of a 32-bit word: (2^52 + v) - 2^52
-__device__ __forceinline__ double w2d(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 
 template <int K, int M>
 __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const FastLuts& L, int ws, int b, Acc& acc) {
@@ -308,8 +306,10 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
     uint32_t seen = 0;
     int next_ok = ws + K - 1;
     // tallies of this item as exact integer-valued doubles (< 2^53): they accumulate on the FP64 pipe
-    double d_kl = 0, d_kh = 0, d_ml = 0, d_mh = 0, d_nk = 0;
-    uint32_t n_nrc = 0;
+    // tallies of this item: integer adds measured 11 % faster than exact-double accumulation on the FP64 pipe
+    // (the kernel is issue-slot bound: the doubles cost extra register-pair moves)
+    uint64_t s_kl = 0, s_ml = 0;                     // sums of the low words (carries kept)
+    uint32_t s_kh = 0, s_mh = 0, n_k = 0, n_nrc = 0; // sums of the high words are needed mod 2^32 only
     uint64_t cur[W + 1], suf[W + 1], pre = 0;
 #pragma unroll
     for (int i = 0; i <= W; i++) { cur[i] = 0; suf[i] = 0; }
@@ -329,10 +329,10 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
         const bool lt = lt62(f, r);                     // ties => was_rc = true (kmer.rs:124-128)
         const uint64_t c = lt ? f : r;
         if (emit) {
-            d_kl += w2d((uint32_t)c); d_kh += w2d((uint32_t)(c >> 32));
-            d_nk += 1.0;
+            s_kl += (uint32_t)c; s_kh += (uint32_t)(c >> 32);
+            n_k++;
             n_nrc += lt ? 1u : 0u;
-            if (MINI) { d_ml += w2d((uint32_t)win); d_mh += w2d((uint32_t)(win >> 32)); }
+            if (MINI) { s_ml += (uint32_t)win; s_mh += (uint32_t)(win >> 32); }
         }
     };
 
@@ -367,10 +367,10 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
         }
     }
     if (seen & 0x80u) return false;                  // a deleted byte inside the item: not this walker's business
-    const uint64_t nk = (uint64_t)d_nk;
+    const uint64_t nk = n_k;
     acc.n_kmers += nk; acc.n_not_rc += n_nrc;
-    acc.ksum_lo += (uint64_t)d_kl + ((uint64_t)d_kh << 32);
-    if (MINI) { acc.n_mini += nk; acc.msum += (uint64_t)d_ml + ((uint64_t)d_mh << 32); }
+    acc.ksum_lo += s_kl + ((uint64_t)s_kh << 32);
+    if (MINI) { acc.n_mini += nk; acc.msum += s_ml + ((uint64_t)s_mh << 32); }
     return true;
 }
 
