@@ -4,17 +4,18 @@
 //   + normalize (sequence.rs:19-62) + reverse_complement (sequence.rs:67-105,202-208)
 //   + CanonicalKmers (kmer.rs:84-129) + BitNuclKmer/minimizer (bitkmer.rs:26-162)
 //
-// Persistent CTAs claim 48 KiB tiles in order (atomic ticket).  Per tile:
+// Persistent CTAs (9 walker warps + 1 coordinator warp, 2 per SM) take tiles of <= 84 KiB round-robin.  Per tile:
 //   P0  the tile (+128 B back halo) is brought into shared memory by one cp.async.bulk (TMA 1-D
-//       bulk copy, SASS UBLKCP) completing on an mbarrier;
-//   P1  every thread scans one 256 B row for '\n' with 32-bit SIMD-in-register tests (rotated
+//       bulk copy, SASS UBLKCP) completing on an mbarrier; the coordinator prefetches the next tile into L2;
+//   P1  every walker thread scans 256 B rows for '\n' with 32-bit SIMD-in-register tests (rotated
 //       word order => bank-conflict free);
-//   P2  block scan -> sorted newline list; the tile's aggregate (newline count, last four newline
-//       positions, FASTA header state) is published and the global prefix is obtained by
-//       decoupled look-back (single pass: the input is read from HBM exactly once);
-//   P3  line roles (FASTQ: newline ordinal mod 4; FASTA: '>' at line start) -> validation events,
-//       n_records / n_bases, and one sequential "walker" per sequence-line fragment: 2-bit rolling
-//       forward / reverse-complement words, canonical select, sliding-window (van Herk) minimizer;
+//   P2  block scan -> sorted newline list; the coordinator warp publishes the tile's aggregate (newline
+//       count, last four newline positions, FASTA header state) and obtains the global prefix by
+//       decoupled look-back, 32 predecessors per step (single pass: the input is read from HBM once);
+//   P3  line roles (FASTQ: newline ordinal mod 4 — walkers start on a locally inferred phase that the
+//       coordinator verifies; FASTA: '>' at line start) -> validation events, n_records / n_bases, and one
+//       sequential "walker" per sequence-line fragment: 2-bit rolling forward / reverse-complement words,
+//       canonical select, sliding-window (van Herk) minimizer;
 //   P4  per-thread tallies stay in registers across tiles; one block reduction + 9 atomics per CTA.
 // Anything the fast path cannot prove clean (parse error, > NLMAX newlines in a tile, whitespace
 // runs longer than the halo) raises a flag and the host re-runs the exact materialising path.
@@ -291,7 +292,7 @@ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8
 struct FastLuts {
     const uint8_t* cls;      // 0..3 code, 4 = kept non-ACGT, >= 0x80 = deleted byte
     const uint32_t* rins;    // ((3 - code) << (2(K-1) - 32)) : the complement base entering the high word of R
-    uint32_t one;            // 1, as a run-time value (keeps mad.wide from being strength-reduced to IADD3 pairs)
+    uint32_t one;            // (unused)
 };
 __device__ __forceinline__ bool lt62(uint64_t a, uint64_t b) { return __longlong_as_double((long long)a) < __longlong_as_double((long long)b); }
 

@@ -382,3 +382,29 @@ def test_cpp_host_mirror(tmp_path):
     out = subprocess.run([exe, str(fa)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "738580 bases" in out.stdout and "8108 AAAAs" in out.stdout
+
+
+def test_alternative_kernel_paths_agree(tmp_path):
+    """The non-speculative general kernel (NTGPU_NO_SPEC=1: what a mis-speculated call is re-run with) and the opt-in
+    warp-specialised short-read kernel (NTGPU_WS=1) must produce the same tallies as the default path and the oracle."""
+    import json, os, subprocess, sys
+    from conftest import ROOT
+    script = tmp_path / "alt.py"
+    script.write_text(
+        "import sys, json, os\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, 'tests'))\n"
+        "import needletail_b200 as nt, oracle_lib as O\n"
+        "from conftest import load_fixtures\n"
+        "ctx = nt.Context(0)\n"
+        "fq = O.gen_fastq(0x5EED0004, 0, 30000, 150, 655).tobytes()\n"
+        "crlf = fq[:316 * 2000].replace(b'\\n', b'\\r\\n')\n"
+        "out = []\n"
+        "for data in (fq, fq[:-1], crlf, load_fixtures()['data/PRJNA271013_head.fq'], fq[:316 * 900] + b'X' + fq[316 * 900 + 1:]):\n"
+        "    for k, m in ((31, 21), (21, 11), (31, 0), (15, 9)):\n"
+        "        t = ctx.tally(data, k=k, m=m); e = O.tally_fastx(data, k=k, m=m)\n"
+        "        out.append(all(t[key] == e[key] for key in e))\n"
+        "print(json.dumps(out))\n")
+    for env in ({"NTGPU_NO_SPEC": "1"}, {"NTGPU_WS": "1"}, {}):
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert all(json.loads(r.stdout.strip().splitlines()[-1])), (env, r.stdout)
