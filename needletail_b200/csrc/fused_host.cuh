@@ -23,7 +23,7 @@ struct FusedState {
     bool pending = false;
     fused::Params P{};
     ntg_tally_config cfg{};
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_ready = nullptr;
     cudaEvent_t ev_chunk[FUSED_MAX_LAUNCHES] = {};
     uint8_t* feed_buf = nullptr; size_t feed_cap = 0;   // device staging for host feeds
     const uint8_t* host_bytes = nullptr;                // when the call was fed from host memory
@@ -71,6 +71,7 @@ static int fused_init(ntg_ctx* ctx) {
     NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_ctrl, sizeof(FusedControl)));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k0));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k1));
+    NTG_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_ready, cudaEventDisableTiming));
     for (auto& e : st->ev_chunk) NTG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     using namespace fused;
 #define NTG_X(k) (fused_kernel_t)k,
@@ -104,6 +105,7 @@ static void fused_destroy(ntg_ctx* ctx) {
     cudaFree(st->slots); cudaFree(st->ctrl); cudaFree(st->final_state); cudaFreeHost(st->h_ctrl); cudaFree(st->feed_buf);
     if (st->ev_k0) cudaEventDestroy(st->ev_k0);
     if (st->ev_k1) cudaEventDestroy(st->ev_k1);
+    if (st->ev_ready) cudaEventDestroy(st->ev_ready);
     for (auto& e : st->ev_chunk) if (e) cudaEventDestroy(e);
     delete st; ctx->fused = nullptr;
 }

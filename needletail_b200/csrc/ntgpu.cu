@@ -319,7 +319,7 @@ int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tall
         tiles_per_chunk = (num_tiles + FUSED_MAX_LAUNCHES - 1) / FUSED_MAX_LAUNCHES;
     // the copy stream must not overwrite feed_buf while an earlier call's kernels still read it, and the
     // control block reset (compute stream) must precede the first launch: both are stream-ordered here.
-    cudaEvent_t ev_ready = ctx->events[63];
+    cudaEvent_t ev_ready = st->ev_ready;
     int s = NTG_OK;
     cudaError_t e = cudaEventRecord(ev_ready, ctx->stream);
     if (!e) e = cudaStreamWaitEvent(ctx->copy_stream, ev_ready, 0);
