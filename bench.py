@@ -129,11 +129,14 @@ def run_reference(args):
     L, k, m = args.read_len, args.k, args.m
     cores = os.cpu_count() or 1
     rb = 2 * L + 16
-    probe = O.gen_fastq(SEED, 0, 20000, L, 0, nthreads=min(cores, 8))
-    _, secs = O.bench_fastq(probe, rb, 1, k, m)
-    rate1 = 20000 * L / max(secs, 1e-6)
+    # size one step from a short all-threads probe so that the whole --steps/--warmup run takes about 90 s
+    nprobe = cores * 4000
+    probe = O.gen_fastq(SEED, 0, nprobe, L, 0, nthreads=cores)
+    O.bench_fastq(probe, rb, cores, k, m)
+    _, secs = O.bench_fastq(probe, rb, cores, k, m)
+    rate_n = nprobe * L / max(secs, 1e-6)                    # bases/s on all host threads
     total_steps = args.steps + args.warmup
-    nrec = int(min(60.0 / total_steps * rate1 * min(cores, 64) * 0.5 / L, (2 << 30) // rb))     # whole run ~1 min
+    nrec = int(min(90.0 / total_steps * rate_n / L, (2 << 30) // rb))
     nrec = max(nrec - nrec % cores, cores * 1000)
     buf = O.gen_fastq(SEED, 0, nrec, L, 0, nthreads=cores)
     for _ in range(args.warmup):
@@ -144,7 +147,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * nrec * L / dt / 1e9
     sample = f"{nrec} records x {L} bp per step, {cores} host threads, C++ oracle port of the reference loop (Rust toolchain absent)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -153,7 +156,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def run_ours(args):
@@ -270,7 +273,7 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
@@ -279,10 +282,31 @@ def run_ours(args):
                        "reads_per_gpu": nrec, "l2": "input (31.6 GB) >> L2 (126 MB): no flush needed", "parallelism": f"records sharded x{world}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "tallies": tallies,
-        }))
+        })
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr; the one JSON line is written
+    to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -301,6 +325,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)          # timing hygiene: at least three untimed passes
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
