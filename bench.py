@@ -241,10 +241,15 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         import ctypes as C
-        host_rec = min(nrec, (args.e2e_host_gib << 30) // rb)
-        hbytes = host_rec * rb
-        hp = C.c_void_p()
-        assert ctx.lib.ntg_alloc_pinned(hbytes, C.byref(hp)) == 0
+        gib = args.e2e_host_gib
+        while True:                                              # pinned host buffer: halve until the box grants it
+            host_rec = min(nrec, (gib << 30) // rb)
+            hbytes = host_rec * rb
+            hp = C.c_void_p()
+            if ctx.lib.ntg_alloc_pinned(hbytes, C.byref(hp)) == 0:
+                break
+            assert gib > 1, "cannot pin even 1 GiB of host memory"
+            gib //= 2
         ctx.lib.ntg_memcpy_d2h(ctx.h, hp, dbuf, hbytes)          # the host copy of the first host_rec records
         ctx.device_free(dbuf); dbuf = None                       # the call owns its own device staging
         calls = (nrec + host_rec - 1) // host_rec                # the host set is fed repeatedly until the shape is covered
