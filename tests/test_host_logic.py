@@ -105,3 +105,15 @@ def test_two_rank_gloo_sharded_tallies(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_lookback_state_monoid(tmp_path):
+    """combine()/identity_state() of the fused kernel's carried scan state form a monoid and folding per-span aggregates
+    equals the state of the whole span (host build of the very same header, 20 000 random strings)."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "test_state_monoid")
+    subprocess.check_call([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "test_state_monoid.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "state monoid ok" in out.stdout, out.stdout + out.stderr
