@@ -11,6 +11,8 @@
 // benches/benchmark.rs:43-44,66-67,151,166,180 (570 records / 738 580 bases /
 // 718 007 k-mers / 350 983 forward-canonical on tests/data/28S.fasta).
 // The Rust reference itself cannot be built here (no rustc/cargo in the image).
+// ntref_incremental.hpp restates the readers' incremental buffer management; tests/test_oracle_incremental.py
+// shows the whole-buffer parsers below give the same results for every buffer capacity.
 //
 // All `ref:` citations are relative to /root/reference/.
 #pragma once

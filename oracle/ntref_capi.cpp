@@ -1,6 +1,7 @@
 // ntref_capi.cpp — flat C ABI over the CPU oracle (ntref.hpp) for ctypes.
 // ORACLE / test infrastructure only: see the header of ntref.hpp.
 #include "ntref.hpp"
+#include "ntref_incremental.hpp"
 #include "synth.hpp"
 
 #include <algorithm>
@@ -89,10 +90,25 @@ uint64_t ntref_bytes_to_bitmer(const uint8_t* s, size_t n) { return bytes_to_bit
 // {start,id_b,id_e,seq_b,seq_e,qual_b,qual_e,all_e,num_bases,pos_line,pos_byte,0}.
 // info (u64[8]): {format, line_ending, err_kind, err_line, err_has_id, final_line, final_byte, 0}
 // Returns the number of records parsed before the first error / EOF.
+static size_t export_parse(const ParseResult& pr, uint64_t* recs, size_t cap, uint64_t* info, char* err_id, size_t err_id_cap);
+
+// Same output, but through the reference's incremental readers (buffer of `capacity` bytes that is refilled,
+// shifted and grown; the underlying Read hands out at most `max_read` bytes per call).
+size_t ntref_parse_fastx_incremental(const uint8_t* buf, size_t n, size_t capacity, size_t max_read, uint64_t* recs, size_t cap,
+                                     uint64_t* info, char* err_id, size_t err_id_cap) {
+    ParseResult pr;
+    parse_fastx_incremental(buf, n, capacity, max_read ? max_read : (size_t)-1, pr);
+    return export_parse(pr, recs, cap, info, err_id, err_id_cap);
+}
+
 size_t ntref_parse_fastx(const uint8_t* buf, size_t n, uint64_t* recs, size_t cap, uint64_t* info,
                          char* err_id, size_t err_id_cap) {
     ParseResult pr;
     parse_fastx(buf, n, pr);
+    return export_parse(pr, recs, cap, info, err_id, err_id_cap);
+}
+
+static size_t export_parse(const ParseResult& pr, uint64_t* recs, size_t cap, uint64_t* info, char* err_id, size_t err_id_cap) {
     size_t c = pr.records.size();
     for (size_t i = 0; i < c && i < cap; i++) {
         const Record& r = pr.records[i];

@@ -44,6 +44,8 @@ def lib():
         L.ntref_bytes_to_bitmer.argtypes = [u8p, sz]; L.ntref_bytes_to_bitmer.restype = C.c_uint64
         L.ntref_parse_fastx.argtypes = [C.c_void_p, sz, C.c_void_p, sz, C.c_void_p, C.c_char_p, sz]
         L.ntref_parse_fastx.restype = sz
+        L.ntref_parse_fastx_incremental.argtypes = [C.c_void_p, sz, sz, sz, C.c_void_p, sz, C.c_void_p, C.c_char_p, sz]
+        L.ntref_parse_fastx_incremental.restype = sz
         L.ntref_tally_fastx.argtypes = [C.c_void_p, sz, C.c_uint, C.c_uint, C.c_int, u8p, C.c_void_p]
         L.ntref_tally_fastx.restype = C.c_int
         L.ntref_bench_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_void_p]
@@ -155,15 +157,20 @@ class Parsed:
     pass
 
 
-def parse_fastx(data: bytes, cap=None):
-    """Whole-buffer parse.  -> object with .format .line_ending .records (list of dict) .err (kind,line,id)"""
+def parse_fastx(data: bytes, cap=None, capacity=None, max_read=0):
+    """Whole-buffer parse (capacity=None) or the reference's incremental readers with a `capacity`-byte buffer.
+    -> object with .format .line_ending .records (list of dict) .err (kind,line,id)"""
     arr = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
     if cap is None:
         cap = data.count(b"\n") + 2
     recs = np.zeros((cap, 12), dtype=np.uint64)
     info = np.zeros(8, dtype=np.uint64)
     eid = C.create_string_buffer(512)
-    c = lib().ntref_parse_fastx(arr.ctypes.data, len(data), recs.ctypes.data, cap, info.ctypes.data, eid, 512)
+    if capacity is None:
+        c = lib().ntref_parse_fastx(arr.ctypes.data, len(data), recs.ctypes.data, cap, info.ctypes.data, eid, 512)
+    else:
+        c = lib().ntref_parse_fastx_incremental(arr.ctypes.data, len(data), capacity, max_read, recs.ctypes.data, cap,
+                                                info.ctypes.data, eid, 512)
     p = Parsed()
     p.format = FMT[int(info[0])]; p.line_ending = LE[int(info[1])]
     p.err_kind = ERR[int(info[2])]; p.err_line = int(info[3])
