@@ -36,6 +36,7 @@ constexpr int SEG = 512;                 // long lines are cut into SEG-byte pie
 constexpr int CHUNK = 1;                 // tiles claimed per ticket. (>1 chains prefixes inside a CTA but serialises chunks:
                                          // a chunk's first tile then waits for the LAST tile of the previous chunk - measured 3700x slower)
 constexpr int LONGMAX = TILE / SEG + 2;
+constexpr int LB_GMAX = 12;              // look-back: at most this many tiles per lane and step (one step spans <= 384 tiles)
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
 
@@ -92,6 +93,7 @@ struct Params {
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
     int has_query;
     uint32_t one;                      // == 1 (run-time constant for mad.wide)
+    uint32_t lb_g;                     // look-back: tiles per lane and step (window = 32 * lb_g tiles), 1..LB_GMAX
     uint32_t spec;                     // FASTQ: walkers start on a locally inferred line phase while the coordinator warp
                                        // does the look-back; a wrong guess raises FLAG_SPEC_MISS and the host re-runs with spec = 0
     uint64_t q_lo, q_hi;
@@ -147,6 +149,7 @@ struct __align__(16) Smem {
     uint32_t rstart[NLMAX + 8];        // FASTA: per line, tile-relative (+HALO) start of its sequence region
     uint8_t lut[256];                  // 0..3 ACGT, 4 kept non-ACGT, 0x85 deleted (space/tab), 0x86 deleted (\r \n)
     uint32_t rins[256];                // fast walker: complement base pre-shifted into the high word of R
+    uint32_t comb[256];                // clean walker: lut | rins in one word
     uint64_t bar;
     uint32_t warp_tmp[NT / 32 + 2];
     uint64_t red[NT / 32][9];
@@ -189,6 +192,35 @@ __device__ __forceinline__ uint32_t block_incl_max(uint32_t v, uint32_t* tmp) { 
     return r;
 }
 
+// ---- P1 helper: newlines of one 256 B row ---------------------------------------------------
+// cnt = number of '\n' bytes, mask bit w = word w of the row holds at least one.  Sixteen 128-bit loads; at step j a
+// lane reads 16 B column (j + lane) & 15, so the eight lanes of a quarter-warp (rows are 256 B apart) hit eight
+// different bank groups.  Branch-free: per word an exact SIMD-in-register byte test, a byte-lane counter and one
+// predicated OR with a compile-time bit; the lane's rotation is undone once at the end.
+__host__ __device__ __forceinline__ void scan_row(const uint32_t* __restrict__ row, uint32_t lane, uint32_t& cnt, uint64_t& mask) {
+    static_assert(ROWB == 256, "scan_row: 16 x 16 B");
+    const uint4* __restrict__ row4 = reinterpret_cast<const uint4*>(row);
+    uint32_t acc = 0, mlo = 0, mhi = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint4 v = row4[(j + lane) & 15u];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t x = w[q] ^ 0x0A0A0A0Au;
+            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;    // 0x80 in every byte that is exactly '\n'
+            acc += z >> 7;                                                              // <= 64 per byte lane
+            const int bit = j * 4 + q;
+            if (z) { if (bit < 32) mlo |= 1u << (bit & 31); else mhi |= 1u << (bit & 31); }
+        }
+    }
+    const uint32_t t = (acc & 0x00FF00FFu) + ((acc >> 8) & 0x00FF00FFu);
+    cnt = (t & 0xFFFFu) + (t >> 16);
+    const uint64_t m = ((uint64_t)mhi << 32) | mlo;
+    const uint32_t rot = (4u * lane) & 63u;                                            // step j saw column (j + lane) & 15
+    mask = rot ? ((m << rot) | (m >> (64u - rot))) : m;
+}
+
 // =============================================================================== the walker
 // Processes the sequence bytes sb[a..b) (tile-relative; sb[-HALO..-1] is the back halo) of one
 // sequence-line fragment.  `lo` = lowest index the warm-up may read; lo_exact tells whether lo is the
@@ -198,7 +230,7 @@ __device__ __forceinline__ uint32_t block_incl_max(uint32_t v, uint32_t* tmp) { 
 //   MINI : also bit_kmers(k,false) -> bitkmer::minimizer(m)      (KW == 1 only)
 //   W    : compile-time window k-m+1 (0 = run-time window, arrays indexed dynamically)
 // warm-up: step back from a over at most k-1 kept good bases, not below lo; returns where to start walking
-__device__ __forceinline__ int find_ws(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int a, int lo, bool lo_exact,
+__host__ __device__ __forceinline__ int find_ws(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int a, int lo, bool lo_exact,
                                        int k, uint32_t& slow) {
     int ws = a, got = 0, p = a - 1;
     bool stopped = false;
@@ -213,7 +245,7 @@ __device__ __forceinline__ int find_ws(const uint8_t* __restrict__ sb, const uin
 }
 
 template <int KW, bool MINI, int W>
-__device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int ws, int a, int b,
+__host__ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int ws, int a, int b,
                                      const Params& P, Acc& acc, bool count_bases) {
     const int k = (int)P.k;
     uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;              // forward / reverse-complement words (x1 = high word, KW == 2)
@@ -289,15 +321,26 @@ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8
 //  - checksums are carried per item as a 64-bit sum of the low words and a 32-bit sum of the high words
 //    (3 integer adds per value) and folded when the item ends;
 //  - non-ACGT bases never branch: they only push `next_ok`, the first index where a k-mer may end.
+#ifndef NTG_BAIL_VOTE
+#define NTG_BAIL_VOTE 1                              // walk_clean leaves early on a warp vote: 0 never, 1 after the head, 2 after every block
+#endif
+struct FalseT { static constexpr bool value = false; };
+struct TrueT { static constexpr bool value = true; };
 struct FastLuts {
     const uint8_t* cls;      // 0..3 code, 4 = kept non-ACGT, >= 0x80 = deleted byte
     const uint32_t* rins;    // ((3 - code) << (2(K-1) - 32)) : the complement base entering the high word of R
-    uint32_t one;            // (unused)
+    const uint32_t* comb;    // cls | rins in one word (walk_clean: one table look-up per base)
 };
-__device__ __forceinline__ bool lt62(uint64_t a, uint64_t b) { return __longlong_as_double((long long)a) < __longlong_as_double((long long)b); }
+__host__ __device__ __forceinline__ bool lt62(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)a) < __longlong_as_double((long long)b);
+#else
+    return a < b;                                    // (host build of the walkers: tests/cpp/test_walkers.cu)
+#endif
+}
 
 template <int K, int M>
-__device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const FastLuts& L, int ws, int b, Acc& acc) {
+__host__ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const FastLuts& L, int ws, int b, Acc& acc, uint32_t* seen_out = nullptr) {
     static_assert(K >= 17 && K <= 31 && M >= 0 && M <= K, "fast walker shape");
     constexpr bool MINI = M > 0;
     constexpr int W = MINI ? K - M + 1 : 1;
@@ -339,11 +382,12 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
 
     // phase 1: the first M-1 bases only feed F / R (no m-mer is complete, no k-mer can end)
     {
-        const int e1 = min(b, ws + (MINI ? M - 1 : K - 1));
+        const int e0 = ws + (MINI ? M - 1 : K - 1), e1 = b < e0 ? b : e0;
         for (; p < e1; p++) roll(p);
     }
     // phase 2: van Herk blocks of W m-mer scores
     while (p < b) {
+        if (seen & 0x80u) return false;              // (usually a newline inside the warm-up: leave at once)
         const bool full = p + W <= b;
 #pragma unroll
         for (int i = 0; i < W; i++) {
@@ -368,10 +412,134 @@ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ sb, const 
         }
     }
     if (seen & 0x80u) return false;                  // a deleted byte inside the item: not this walker's business
+    if (seen_out) *seen_out = seen;
     const uint64_t nk = n_k;
     acc.n_kmers += nk; acc.n_not_rc += n_nrc;
     acc.ksum_lo += s_kl + ((uint64_t)s_kh << 32);
     if (MINI) { acc.n_mini += nk; acc.msum += s_ml + ((uint64_t)s_mh << 32); }
+    return true;
+}
+
+
+// =============================================================================== the clean walker
+// The common case made cheap: the item bytes sb[ws..b) are all ACGT/acgt.  Anything else (a kept non-ACGT base, a
+// deleted byte) only sets a bit in `seen`; the function then returns false with acc untouched and the caller redoes
+// the item with walk_fast / walk.  Knowing that every base is good removes the per-base "may a k-mer end here" logic:
+// exactly the positions >= ws + K - 1 emit, so the walk is  head (K-1 bases, nothing emitted)  +  unconditional blocks.
+//  - one combined table word per base (class bits 0..7, complement base pre-shifted for the high word of R);
+//  - F is kept unmasked (old bases fall off the top of the 64-bit word), masked copies feed the compares;
+//  - the van Herk buffers share ONE array: buf[i] holds the current block's scores below the running position and the
+//    previous block's suffix minima above it (the body is rotated so that the suffix pass follows element W-1);
+//  - checksums are plain wrapping 64-bit adds (2 instructions per value), the k-mer count is b - (ws + K - 1).
+template <int K, int M>
+__host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, Acc& acc) {
+    static_assert(K >= 21 && K <= 31 && M >= 0 && M <= K, "clean walker shape (class bits 0..7 must not overlap the R insert)");
+    constexpr bool MINI = M > 0;
+    constexpr int W = MINI ? K - M + 1 : 1;
+    constexpr int B = MINI ? W : 8;                  // bases per unrolled block
+    constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
+    constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
+    constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
+    constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
+    constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
+    uint64_t f = 0, r = 0, s_k = 0, s_m = 0, pre = 0;
+    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
+    uint64_t buf[W + 1];
+#pragma unroll
+    for (int i = 0; i <= W; i++) buf[i] = 0;
+    int p = ws;
+
+    // Leave as soon as a lane of the (converged part of the) warp has met a byte this walker cannot handle: the warp then
+    // redoes its items with walk_fast together instead of finishing a walk whose result is thrown away.  A hint only:
+    // exactness rests on each lane's own `seen` test at the end.
+    auto bail = [&]() -> bool {
+#if defined(__CUDA_ARCH__)
+        return __any_sync(__activemask(), (seen & 0x84u) != 0u);
+#else
+        return (seen & 0x84u) != 0u;
+#endif
+    };
+    auto roll = [&](int pp) {
+        const uint32_t u = comb[sb[pp]];
+        seen |= u;
+        f = (f << 2) | (uint64_t)(u & 3u);
+        r = (r >> 2) | ((uint64_t)(u & RMASK) << 32);
+    };
+    // score of the m-mer x ending here: min(x, RC_k(x)), RC_k(x) = R | LMASK (bitkmer.rs:146-162).  RC_k(x) can only be
+    // the smaller one when R < 4^M, i.e. when the last K-M bases are all T (4^-(K-M) per position in random sequence):
+    // RARE shapes take x and only remember the smallest top part of R seen; an item where that ever reached zero
+    // is handed to walk_fast like one with a non-ACGT base.
+    auto score = [&]() -> uint64_t {
+        const uint64_t x = f & MMASK;
+        if (RARE) {
+            const uint32_t top = (2 * M >= 32) ? (uint32_t)(r >> 32) : (uint32_t)(r >> (2 * M));
+            rtop_min = top < rtop_min ? top : rtop_min;
+            return x;
+        }
+        const uint64_t y = r | LMASK;
+        return lt62(x, y) ? x : y;
+    };
+    auto tally = [&](uint64_t win) {
+        const uint64_t fm = f & KMASK;
+        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
+        s_k += lt ? fm : r;
+        n_nrc += lt ? 1u : 0u;
+        if (MINI) s_m += win;
+    };
+    // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
+    auto block = [&](auto check) {
+        constexpr bool CHECK = decltype(check)::value;
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            if (CHECK && p + j >= b) return;
+            roll(p + j);
+            uint64_t win = 0;
+            if (MINI) {
+                const uint64_t sc = score();
+                if (j == 0) {
+                    pre = (W == 1 || lt62(sc, pre)) ? sc : pre;
+                    win = pre;
+                    buf[W - 1] = sc;
+#pragma unroll
+                    for (int q = W - 2; q >= 1; q--) buf[q] = lt62(buf[q], buf[q + 1]) ? buf[q] : buf[q + 1];
+                } else {
+                    const int i = j - 1;
+                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                    win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
+                    buf[i] = sc;
+                }
+            }
+            tally(win);
+        }
+    };
+
+    // head: K-1 bases that cannot end a k-mer — M-1 of them only feed F / R, the other W-1 are the first scores
+    {
+        const int e0 = ws + (MINI ? M - 1 : K - 1), e1 = b < e0 ? b : e0;
+#pragma unroll 4
+        for (; p < e1; p++) roll(p);
+        if (MINI) {
+#pragma unroll
+            for (int i = 0; i < W - 1; i++) {
+                if (p + i < b) {
+                    roll(p + i);
+                    const uint64_t sc = score();
+                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                    buf[i] = sc;
+                }
+            }
+            p += W - 1;
+        }
+    }
+    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
+    while (p + B <= b) { block(FalseT{}); p += B; if (NTG_BAIL_VOTE >= 2 && bail()) return false; }
+    if (p < b) block(TrueT{});
+    if ((seen & 0x84u) || (RARE && rtop_min < RTOP_LIMIT)) return false;
+    const int nk_i = b - (ws + K - 1);
+    const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
+    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
+    acc.ksum_lo += s_k;
+    if (MINI) { acc.n_mini += nk; acc.msum += s_m; }
     return true;
 }
 
@@ -395,6 +563,7 @@ template <bool BLOCKING = true>
 __device__ __forceinline__ bool warp_lookback_try(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, SState& out) {
     SState suffix = identity_state();
     int64_t base = (int64_t)t - 1;
+    uint32_t backoff = 32;                                          // ns; doubles up to 256 (polling costs issue slots and L2 traffic)
     for (;;) {
         const int64_t j = base - (int64_t)lane;
         uint32_t st = 2;                                            // before the first tile: inclusive(identity)
@@ -402,7 +571,7 @@ __device__ __forceinline__ bool warp_lookback_try(const Params& P, uint64_t t, u
         const uint32_t inc_mask = __ballot_sync(0xffffffffu, st == 2), nr_mask = __ballot_sync(0xffffffffu, st == 0);
         const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
         const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if (nr_mask & need) { if (!BLOCKING) return false; __nanosleep(20); continue; }
+        if (nr_mask & need) { if (!BLOCKING) return false; __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
         const int top = first_inc < 32 ? first_inc : 31;
         SState acc = identity_state();                              // lanes above `top` contribute the identity
         if (j >= 0 && (int)lane <= top) acc = ((int)lane == first_inc) ? P.slots[j].inc : P.slots[j].agg;
@@ -424,6 +593,77 @@ __device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uin
     return r;
 }
 
+// Wide look-back (the fused kernel): the CTAs of a persistent grid work on grid-many consecutive tiles at the same time, so
+// the tiles just before t only ever offer AGGREGATES until their own look-backs finish; with a 32-tile window the inclusive
+// prefix then crosses such a wave in grid/32 dependent hops (each: observe, load, reduce, publish - microseconds), and that
+// chain, not the walkers, set the time per wave.  Here lane l covers the G = ceil(grid/32) consecutive tiles
+// base - l*G - g (g = 0 nearest), so one step reaches back into the previous wave, whose inclusive prefixes were
+// published long ago: one hop per wave.  Flags are polled with relaxed loads (no L1 invalidation per poll); one
+// fence orders the payload loads, which bypass L1 (ld.global.cg).
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ SState ld_state_cg(const SState* p) {
+    static_assert(sizeof(SState) == 64, "four 16 B loads");
+    SState r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4* o = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = __ldcg(q + i);
+    return r;
+}
+__device__ __forceinline__ SState warp_lookback_wide(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, int G) {
+    SState suffix = identity_state();
+    int64_t base = (int64_t)t - 1;                                  // nearest predecessor not folded into `suffix` yet
+    uint32_t backoff = 32;
+    for (;;) {
+        const int64_t j0 = base - (int64_t)lane * G;                // this lane: tiles j0, j0-1, ..., j0-G+1
+        uint32_t stv[LB_GMAX];                                      // all flags of this lane in flight together
+#pragma unroll
+        for (int g = 0; g < LB_GMAX; g++) {
+            const int64_t j = j0 - g;
+            uint32_t st = 2;                                        // before the first tile: inclusive(identity)
+            if (g < G && j >= 0) { const uint32_t f = ld_relaxed_u32(&P.slots[j].flag); st = ((f >> 2) == epoch) ? (f & 3u) : 0u; }
+            stv[g] = st;
+        }
+        int g_inc = G, g_ready = 0;                                 // nearest g holding an inclusive prefix; leading published g's
+        bool open = true;
+#pragma unroll
+        for (int g = 0; g < LB_GMAX; g++) {
+            if (g < G && open) {
+                if (stv[g] == 0) open = false;
+                else { g_ready = g + 1; if (stv[g] == 2) { g_inc = g; open = false; } }
+            }
+        }
+        const bool has_inc = g_inc < G, complete = has_inc || g_ready == G;
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, has_inc), ok_mask = __ballot_sync(0xffffffffu, complete);
+        const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
+        const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
+        if (~ok_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
+        __threadfence();                                            // flags observed -> payloads (acquire side)
+        SState acc = identity_state();                              // lanes beyond first_inc contribute the identity
+        if ((int)lane <= first_inc) {
+            const int gtop = ((int)lane == first_inc) ? g_inc : G - 1;
+            for (int g = gtop; g >= 0; g--) {                       // farthest (earliest) tile first
+                const int64_t j = j0 - g;
+                if (j < 0) continue;                                // (identity)
+                const SState sj = ld_state_cg(((int)lane == first_inc && g == g_inc) ? &P.slots[j].inc : &P.slots[j].agg);
+                acc = combine(acc, sj);
+            }
+        }
+        // ordered tree reduction: higher lanes hold EARLIER tiles; combine() is associative
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const SState earlier = shfl_state(acc, (int)lane + d < 32 ? (int)lane + d : (int)lane);
+            if ((int)lane + d < 32) acc = combine(earlier, acc);
+        }
+        acc = shfl_state(acc, 0);
+        suffix = combine(acc, suffix);
+        if (first_inc < 32) return suffix;
+        base -= 32 * (int64_t)G;
+    }
+}
+
 // =============================================================================== the kernel
 __device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
     // global position -> byte, from shared memory when resident, else from global memory
@@ -440,19 +680,46 @@ template <int KW, bool MINI, int W>
 __device__ __noinline__ void walk_slow(const uint8_t* sb, const uint8_t* lut, int ws, int a, int b, const Params& P, Acc& acc, bool count_bases) {
     walk<KW, MINI, W>(sb, lut, ws, a, b, P, acc, count_bases);
 }
+#ifndef NTG_LB_WIDE
+#define NTG_LB_WIDE 0                                // 1: warp_lookback_wide (window 32 * NTGPU_LB_G tiles) instead of the 32-tile look-back.
+#endif                                               //    Measured slower (B200, C2: G=1 396, G=2 401-410, G=10 330 vs 425 Gbases/s): kept for A/B only
+#ifndef NTG_CLEAN
+#define NTG_CLEAN 1                                  // 0: items go straight to walk_fast (the round-1 kernel), for A/B timing
+#endif
+template <int K, int M>
+__device__ __noinline__ bool walk_fast_cold(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, int ws, int b, Acc& acc, uint32_t* seen_out) {
+    FastLuts L{lut, rins, nullptr};
+    return walk_fast<K, M>(sb, L, ws, b, acc, seen_out);
+}
 
-// One sequence-line fragment sb[a..b): warm-up, then the constant-folded walker when this kernel has one
-// (FK > 0) and the item holds no deleted bytes, else the generic walker.
+// One sequence-line fragment sb[a..b): warm-up, then (kernels with a constant-folded shape, FK > 0) the clean walker;
+// items with a non-ACGT base fall to the constant-folded walker that tracks them, items with deleted bytes
+// (whitespace inside the item) and all other shapes to the generic walker.
+// `mode` (per thread, kept across items): non-zero after an item that the clean walker could not take.  While any lane of
+// the warp is in that state the warp skips the clean attempt - on data full of N (BASELINE C4: 78 % of the reads)
+// every warp would otherwise walk each item twice; a clean item puts the lane back.
 template <int KW, bool MINI, int W, int FK, int FM>
-__device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, int a, int b, int lo, bool lo_exact,
-                                         const Params& P, Acc& acc, bool fasta, uint32_t& slow) {
+__device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, const uint32_t* comb, int a, int b, int lo,
+                                         bool lo_exact, const Params& P, Acc& acc, bool fasta, uint32_t& slow, uint32_t& mode) {
     if (b > a && sb[b - 1] == '\r') b--;                   // a trailing '\r' is deleted by normalize: nothing to walk
     const bool had_cr_only = b <= a;
     if (had_cr_only) return;
     const int ws = find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
     if (FK > 0) {
-        FastLuts L{lut, rins, (uint32_t)P.one};
-        if (walk_fast<(FK > 0 ? FK : 17), (FK > 0 ? FM : 0)>(sb, L, ws, b, acc)) {
+        constexpr int CK = FK > 0 ? FK : 21, CM = FK > 0 ? FM : 0;
+        bool done = false;
+        if (NTG_CLEAN && CK >= 21) {
+            if (!__any_sync(__activemask(), mode != 0u)) done = walk_clean<(CK >= 21 ? CK : 21), (CK >= 21 ? CM : 0)>(sb, comb, ws, b, acc);
+            if (!done) {
+                uint32_t seen = 0x80u;
+                done = walk_fast_cold<CK, CM>(sb, lut, rins, ws, b, acc, &seen);
+                mode = seen > 3u ? 1u : 0u;                 // (stays set when walk_fast gave up on a deleted byte)
+            }
+        } else {
+            FastLuts L{lut, rins, comb};
+            done = walk_fast<CK, CM>(sb, L, ws, b, acc);
+        }
+        if (done) {
             if (fasta) acc.n_bases += (uint64_t)(b - a);   // no deleted bytes in [ws,b): every byte is a base
             return;
         }
@@ -466,17 +733,25 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
 // of the first lines that start in this tile ('@' at role 0, '+' at role 2)?  Returns 0..3, or 4 when fewer than four
 // line starts are visible or the evidence is not unique.  Used only to START early; the true phase (newline ordinal
 // from the look-back) is checked afterwards and a mismatch raises FLAG_SPEC_MISS.
+// Must be called by whole (converged) warps: lane j < 8 looks at the j-th visible line start, the evidence is AND-reduced.
 template <typename NLT>
 __device__ __forceinline__ uint32_t guess_phase(const NLT* __restrict__ nl, const uint8_t* __restrict__ sb, uint32_t Cs,
                                                 uint32_t avail, bool line0_starts_here) {
-    uint32_t ok = 0xF, seen = 0;
-    for (uint32_t i = line0_starts_here ? 0u : 1u; i <= Cs && seen < 8; i++, seen++) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = (line0_starts_here ? 0u : 1u) + lane;
+    uint32_t ok = 0xF;
+    bool valid = false;
+    if (lane < 8 && i <= Cs) {
         const uint32_t s = i ? (uint32_t)nl[i - 1] + 1u : 0u;
-        if (s >= avail) break;
-        const uint8_t c = sb[s];
-        ok &= ~((c != '@' ? 1u : 0u) << ((0u - i) & 3u));
-        ok &= ~((c != '+' ? 1u : 0u) << ((2u - i) & 3u));
+        if (s < avail) {                                     // (line starts increase with i: the valid lanes form a prefix)
+            valid = true;
+            const uint8_t c = sb[s];
+            ok &= ~((c != '@' ? 1u : 0u) << ((0u - i) & 3u));
+            ok &= ~((c != '+' ? 1u : 0u) << ((2u - i) & 3u));
+        }
     }
+    const uint32_t seen = (uint32_t)__popc(__ballot_sync(0xffffffffu, valid));
+    ok = __reduce_and_sync(0xffffffffu, ok);
     if (seen < 4 || __popc(ok) != 1) return 4;
     return (uint32_t)__ffs((int)ok) - 1u;
 }
@@ -498,11 +773,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
     for (int i = tid; i < 256; i += NT) {
         const uint8_t c = class_of(i);
         S.lut[i] = c;
-        S.rins[i] = (FK >= 17) ? ((3u - (c & 3u)) << (2 * ((FK >= 17 ? FK : 17) - 1) - 32)) : 0u;
+        const uint32_t ri = (FK >= 17) ? ((3u - (c & 3u)) << (2 * ((FK >= 17 ? FK : 17) - 1) - 32)) : 0u;
+        S.rins[i] = ri;
+        S.comb[i] = ri | c;
     }
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
     __syncthreads();
-    uint32_t parity = 0, slow = 0, my_seq = 0;
+    uint32_t parity = 0, slow = 0, my_seq = 0, mode = 0;
     Acc acc;
     const uint8_t* sb = S.tile;
     const bool fasta = P.format == NTG_FMT_FASTA;
@@ -547,20 +824,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         for (int rd = 0; rd < MAXROUNDS; rd++) {
             cnt[rd] = 0; wmask[rd] = 0;
             const uint32_t rowi = rd * NTW + tid;
-            if (tid < NTW && rowi < nrows) {
-                const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW;
-#pragma unroll 8
-                for (int j = 0; j < ROWW; j++) {
-                    const uint32_t jj = (j + lane) & (ROWW - 1);
-                    const uint32_t x = row[jj] ^ 0x0A0A0A0Au;
-                    if ((x - 0x01010101u) & ~x & 0x80808080u) {             // exact as a boolean: some byte is '\n'
-                        wmask[rd] |= 1ull << jj;
-                        uint32_t z = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                        z = ~(z | x | 0x7F7F7F7Fu);                          // 0x80 in every byte that is exactly '\n'
-                        cnt[rd] += __popc(z);
-                    }
-                }
-            }
+            if (tid < NTW && rowi < nrows) scan_row(reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW, lane, cnt[rd], wmask[rd]);
         }
         // ---- P2: ordered newline list (rows are ordered round-major: one scan of the packed per-round counts)
         static_assert(MAXROUNDS == 2, "packed scan below assumes two rounds");
@@ -631,7 +895,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             }
             __syncwarp();
             if (chained) pre = S.last_inc;
-            else if (t > 0) pre = warp_lookback(P, t, epoch, lane);
+            else if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
             if (lane == 0) {
                 const SState inc = combine(pre, agg);
                 slot->inc = inc;
@@ -744,7 +1008,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                     if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                     int lo; bool lo_exact;
                     fastq_bound(i, a, lo, lo_exact);
-                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, false, slow);
+                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, false, slow, mode);
                 }
             }
         } else {
@@ -779,7 +1043,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                 int lo; bool lo_exact;
                 fasta_bound(i, a, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, true, slow);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, true, slow, mode);
             }
         }
         __syncthreads();
@@ -807,10 +1071,10 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 const int a = la + (int)(pc - S.long_pref[j]) * PSEG, b = min(a + PSEG, lb);
                 int lo; bool lo_exact;
                 if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, a, b, lo, lo_exact, P, acc, fasta, slow);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode);
             }
-        }
-        __syncthreads();
+            __syncthreads();                               // (no long lines: nothing read the tile since the barrier above, and
+        }                                                  //  the reset of S.n_long at the next tile stores the value it holds)
         my_seq++;
     }
 

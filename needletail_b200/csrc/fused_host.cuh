@@ -166,6 +166,11 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
     P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
     P.spec = (allow_ws && format == NTG_FMT_FASTQ && getenv("NTGPU_NO_SPEC") == nullptr) ? 1 : 0;
+    {
+        const char* e = getenv("NTGPU_LB_G");                       // experiment knob: look-back window = 32 * G tiles
+        int g = e ? atoi(e) : 1;
+        P.lb_g = (uint32_t)(g < 1 ? 1 : (g > fused::LB_GMAX ? fused::LB_GMAX : g));
+    }
     P.q_lo = P.q_hi = 0;
     if (cfg->has_query)
         for (uint32_t i = 0; i < cfg->k; i++) {

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(WNT, 3) k_fused_ws(const Params P, const uint6
         }
     } else {
         // ================================================================== walkers
-        const FastLuts L{S.lut, S.rins, 1u};
+        const FastLuts L{S.lut, S.rins, nullptr};
         uint32_t q = 0;                       // stage sequence number holding the first item of my next batch (monotone)
         uint32_t walker_flags = 0;
         long long c_wait = 0, c_work = 0;

@@ -117,3 +117,16 @@ def test_lookback_state_monoid(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "test_state_monoid.cu")], stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "state monoid ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_walkers_match_oracle_on_host(tmp_path):
+    """find_ws / walk / walk_fast / walk_clean of the fused kernel are __host__ __device__: the very same source, compiled
+    for the CPU, must reproduce the oracle's tallies on random lines (clean, non-ACGT, whitespace, T runs), whole and cut
+    into warmed-up fragments (tests/cpp/test_walkers.cu)."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "test_walkers")
+    subprocess.check_call([nvcc, "-std=c++17", "--expt-relaxed-constexpr", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "test_walkers.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "walkers ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

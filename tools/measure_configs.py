@@ -3,6 +3,7 @@
 Not the bench line: a side table for DESIGN.md.  Sizes are reduced where noted so the run stays short.
 
     python tools/measure_configs.py > gpurun_out/configs.json
+    NT_MC_ONLY=0,1,3 NTGPU_SO=needletail_b200/libntgpu_base.so python tools/measure_configs.py     # A/B of an experiment build
 """
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,7 +23,9 @@ CONFIGS = [
 def main():
     ctx = nt.Context(0)
     out = []
-    for name, kind, reads, L, k, m, nth, seed in CONFIGS:
+    only = os.environ.get("NT_MC_ONLY")
+    configs = [CONFIGS[int(i)] for i in only.split(",")] if only else CONFIGS
+    for name, kind, reads, L, k, m, nth, seed in configs:
         rb = 2 * L + 16 if kind == "fastq" else L + 12
         nbytes = reads * rb
         d = ctx.device_alloc(nbytes)
