@@ -235,7 +235,7 @@ def run_ours(args):
                 "traffic": (ratio * nbytes) if ratio else None, "kernel": "fused::k_fused<1,true,11,31,21>", "kernel_ms": kavg,
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "traffic_note": "DRAM bytes per launch = ncu dram read+write bytes per input byte (profiles/traffic.json) x algorithmic bytes",
-                "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~44 SASS instructions per base, of which ~60 % on the 16-lane INT pipe (57 % busy), plus end-of-tile barrier waits behind the look-back (profiles/r1i_*); see DESIGN.md"}
+                "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~44 SASS instructions per base, of which ~60 % on the 16-lane INT pipe (59 % busy), plus end-of-tile barrier waits behind the look-back (profiles/r1j_*); see DESIGN.md"}
 
     # ---- end to end through the host-facing C-ABI call: pinned host FASTQ -> H2D -> fused kernel -> tallies
     e2e = None

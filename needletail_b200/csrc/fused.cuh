@@ -156,6 +156,12 @@ struct __align__(16) Smem {
     SState prefix;                     // exclusive prefix of this tile
     SState last_inc;                   // inclusive prefix of the previous tile of this CTA's chunk
     volatile uint32_t prefix_seq;      // number of tiles of this CTA whose prefix has been resolved by the coordinator
+    // the tile whose look-back the coordinator has deferred by one tile (speculative FASTQ, see P2c); coordinator warp only
+    SState pend_agg;
+    uint64_t pend_t;
+    uint32_t pend_guess, pend_cs, pend_avail, pend_line0;
+    uint32_t pend_nl4[4];              // the tile's first four newline offsets
+    volatile uint32_t pend_valid;
     uint32_t tile_idx;
     uint32_t tile_idx_next;            // ticket of the next tile, claimed by the coordinator during this one
     uint32_t n_long;
@@ -763,6 +769,72 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
     lo = -(int)halo; lo_exact = false;
 }
 
+
+#ifndef NTG_LB_DEFER
+#define NTG_LB_DEFER 1                               // 0: every tile's look-back is resolved inside its own tile (round-1 behaviour), for A/B timing
+#endif
+// Coordinator warp: resolve the tile deferred at the previous P2c — look-back, inclusive prefix, check of the speculated
+// line phase, and the line events (fastq.rs:240-285) of the tile's first four lines, the ones that may need the prefix.
+// The tile's bytes have left shared memory by now: the few bytes involved are read from global memory (L2).
+__device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t epoch, uint32_t lane, Acc& acc, uint32_t& slow) {
+    const uint64_t t = S.pend_t;
+    const SState agg = S.pend_agg;
+    SState pre = identity_state();
+    if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
+    if (lane == 0) {
+        const SState inc = combine(pre, agg);
+        TileSlot* slot = &P.slots[t];
+        slot->inc = inc;
+        __threadfence();
+        st_release_u32(&slot->flag, epoch * 4 + 2);
+        if (t + 1 == P.num_tiles) *P.final_state = inc;
+    }
+    const uint32_t ord0 = (uint32_t)(pre.count & 3);
+    if (S.pend_guess != ord0) slow |= FLAG_SPEC_MISS;
+    const uint32_t Cs = S.pend_cs, avail = S.pend_avail, i = lane;
+    const uint64_t tile_start = t * (uint64_t)P.tile_bytes;
+    if (i < 4 && i <= Cs) {
+        auto nl = [&](uint32_t j) -> uint64_t { return tile_start + S.pend_nl4[j]; };                 // j < min(Cs, 4)
+        auto prev_nl = [&](uint32_t back) -> uint64_t {                                               // `back` newlines before newline i
+            if (i >= back) return nl(i - back);
+            const uint32_t r = back - i - 1;
+            return r < 4 ? pre.last[r] : NONE;
+        };
+        auto cr_before = [&](uint64_t q, uint64_t prevq) -> uint32_t {                                // trim_cr on the line (prevq, q)
+            const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
+            return (q > ls && P.bytes[q - 1] == '\r') ? 1u : 0u;
+        };
+        const uint32_t role = (ord0 + i) & 3;
+        const uint64_t s = i ? nl(i - 1) + 1 : tile_start;
+        const bool starts = (i > 0 || S.pend_line0 != 0) && (s - tile_start) < avail;
+        if (starts) {
+            const uint8_t c = P.bytes[s];
+            if (role == 0 && c != '@') slow |= FLAG_PARSE_ERROR;
+            if (role == 2 && c != '+') slow |= FLAG_PARSE_ERROR;
+        }
+        if (i < Cs) {
+            const uint64_t q = nl(i);
+            if (role == 1) {
+                const uint64_t p1 = prev_nl(1);
+                const uint64_t ls = p1 == NONE ? 0 : p1 + 1;
+                acc.n_bases += (q - ls) - cr_before(q, p1);
+            } else if (role == 3) {
+                const uint64_t q2 = prev_nl(1), q1 = prev_nl(2), q0 = prev_nl(3);
+                if (q2 == NONE || q1 == NONE || q0 == NONE) slow |= FLAG_PARSE_ERROR;
+                else {
+                    const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
+                    const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
+                    if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;
+                    acc.n_records++;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) S.pend_valid = 0;
+    __syncwarp();
+}
+
 template <int KW, bool MINI, int W, int FK, int FM>
 __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
@@ -777,7 +849,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         S.rins[i] = ri;
         S.comb[i] = ri | c;
     }
-    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0; }
     __syncthreads();
     uint32_t parity = 0, slow = 0, my_seq = 0, mode = 0;
     Acc acc;
@@ -876,7 +948,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             last_start1 = (uint32_t)S.bcast[0];
         }
 
-        // ---- P2c: publish aggregate, decoupled look-back (coordinator warp, 32 predecessors per step), publish inclusive prefix
+        // ---- P2c: publish aggregate, decoupled look-back (coordinator warp, 32 predecessors per step), publish inclusive prefix.
+        // Speculative FASTQ: when the tile offers a unique local line phase nobody in this CTA needs the tile's prefix
+        // now, so its look-back is DEFERRED by one tile: the coordinator publishes the aggregate at once, then resolves the
+        // tile it deferred last time (whose predecessors published their aggregates a whole tile ago: no waiting on the
+        // skew between CTAs, and the end-of-tile barrier no longer waits for a look-back that has just begun), verifies
+        // that tile's guess and does the events of its first four lines from global memory.
+        const uint32_t guess = spec ? guess_phase(S.nl, sb, Cs, avail, line0_starts_here) : 4u;
+        const bool defer = NTG_LB_DEFER && spec && guess != 4u && t > 0;      // (tile 0 has nothing to look back at)
         SState pre = identity_state();
         if (is_coord) {
             SState agg = identity_state();
@@ -894,18 +973,30 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 st_release_u32(&slot->flag, epoch * 4 + 1);
             }
             __syncwarp();
-            if (chained) pre = S.last_inc;
-            else if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
+            if (S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);
+            if (defer) {
+                if (lane == 0) {
+                    S.pend_agg = agg; S.pend_t = t; S.pend_guess = guess; S.pend_cs = Cs; S.pend_avail = avail;
+                    S.pend_line0 = line0_starts_here ? 1u : 0u;
+                    for (uint32_t j = 0; j < 4; j++) S.pend_nl4[j] = j < Cs ? S.nl[j] : 0u;
+                    S.pend_valid = 1;
+                }
+            } else {
+                if (chained) pre = S.last_inc;
+                else if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
+                if (lane == 0) {
+                    const SState inc = combine(pre, agg);
+                    slot->inc = inc;
+                    __threadfence();
+                    st_release_u32(&slot->flag, epoch * 4 + 2);
+                    S.prefix = pre;
+                    S.last_inc = inc;
+                    if (t + 1 == P.num_tiles) *P.final_state = inc;
+                    __threadfence_block();
+                    S.prefix_seq = my_seq + 1;
+                }
+            }
             if (lane == 0) {
-                const SState inc = combine(pre, agg);
-                slot->inc = inc;
-                __threadfence();
-                st_release_u32(&slot->flag, epoch * 4 + 2);
-                S.prefix = pre;
-                S.last_inc = inc;
-                if (t + 1 == P.num_tiles) *P.final_state = inc;
-                __threadfence_block();
-                S.prefix_seq = my_seq + 1;
                 // next tile of this CTA: pull it into L2 while the walkers work on this one
                 const uint64_t tn = t + gridDim.x;
                 if (tn < tile_end) {
@@ -916,7 +1007,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             }
             __syncwarp();
         }
-        bool have_pre = is_coord;
+        bool have_pre = is_coord && !defer;
         if (!spec) { __syncthreads(); pre = S.prefix; have_pre = true; }      // everyone needs the prefix before going on
         // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
         auto prev_nl = [&](uint32_t i, uint32_t back) -> uint64_t {
@@ -953,7 +1044,6 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         if (!fasta) {
             // ---------------------------------------------------------------------------- FASTQ
             uint32_t ord0;
-            const uint32_t guess = spec ? guess_phase(S.nl, sb, Cs, avail, line0_starts_here) : 4u;
             if (have_pre) ord0 = (uint32_t)(pre.count & 3);
             else if (guess != 4) ord0 = guess;
             else {                                                      // no unique local evidence: wait for the coordinator
@@ -994,7 +1084,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             // coordinator warp (which has the prefix) takes the lines that may need it — the first four of the tile —
             // and each walker takes the lines >= 4 of "its" record, whose previous newlines are all in the tile's list.
             if (!spec) { for (uint32_t i = tid; i <= Cs; i += NT) line_events(i); }
-            else if (is_coord) { for (uint32_t i = lane; i <= Cs && i < 4; i += 32) line_events(i); }
+            else if (is_coord && have_pre) { for (uint32_t i = lane; i <= Cs && i < 4; i += 32) line_events(i); }   // (deferred: resolve_pending)
             // (B) sequence lines only: walker thread j takes the j-th role-1 line of the tile (every 4th line)
             const uint32_t i_first = (1u - ord0) & 3u;
             if (!is_coord) {
@@ -1077,6 +1167,8 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         }                                                  //  the reset of S.n_long at the next tile stores the value it holds)
         my_seq++;
     }
+
+    if (is_coord && S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);      // the last deferred tile of this CTA
 
     // ---- P4: block reduction of the register tallies, 9 atomics per CTA
     uint64_t v[9] = {acc.n_records, acc.n_bases, acc.n_kmers, acc.n_not_rc, acc.ksum_lo, acc.ksum_hi, acc.n_query, acc.n_mini, acc.msum};
