@@ -3,7 +3,8 @@
 The product is ``libntgpu.so`` (include/ntgpu.h).  This module is the thin Python face of it, with
 the function names of the reference's own Python module (src/python.rs:429-438:
 ``parse_fastx_file``, ``parse_fastx_string``, ``normalize_seq``, ``reverse_complement``,
-``decode_phred`` is host-only and omitted) plus batch forms of the ``Sequence`` trait methods
+``decode_phred`` — the last one is a byte subtraction and stays on the host, as in the reference)
+plus batch forms of the ``Sequence`` trait methods
 (src/sequence.rs:156-253) and the fused hot-path call.  There is no CPU fallback: importing works
 anywhere, but every call needs a B200 (``Context()`` raises ``NtgError`` otherwise).
 """
@@ -520,3 +521,15 @@ def normalize_seq(seq, iupac=False, ctx=None):
 def reverse_complement(seq, ctx=None):
     out = (ctx or default_context()).reverse_complement([seq.encode() if isinstance(seq, str) else seq])
     return out[0].decode()
+
+
+def decode_phred(qual, base_64=False):
+    """quality::decode_phred (src/quality.rs:15-28) with the signature and error of the reference's Python module
+    (src/python.rs:416-427): Phred+33 (or +64) characters -> tuple of scores; a character below the offset raises
+    ValueError.  Host arithmetic — off the device path, like the reference's."""
+    q = np.frombuffer(qual.encode() if isinstance(qual, str) else bytes(qual), dtype=np.uint8)
+    offset = 64 if base_64 else 33
+    bad = np.flatnonzero(q < offset)
+    if bad.size:
+        raise ValueError("Invalid Phred quality: character '%s' cannot be decoded with offset '%d'" % (chr(int(q[bad[0]])), offset))
+    return tuple(int(v) for v in (q - offset))

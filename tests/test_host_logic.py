@@ -130,3 +130,16 @@ def test_walkers_match_oracle_on_host(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "test_walkers.cu")], stderr=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "walkers ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_decode_phred_vectors():
+    """quality.rs:34-64 and test_python.py:152-168 (host-only function of the Python face)."""
+    import needletail_b200 as nt
+    want = (2, 27, 14, 27, 14, 33, 33, 37, 37, 37, 33, 37, 27)
+    assert nt.decode_phred("#</</BBFFFBF<") == want
+    assert nt.decode_phred("B[N[Naaeeeae[", base_64=True) == want
+    assert nt.decode_phred("") == ()
+    with pytest.raises(ValueError, match="character ' ' cannot be decoded with offset '33'"):
+        nt.decode_phred("#</</BBFFFBF ")
+    with pytest.raises(ValueError, match=r"character '\?' cannot be decoded with offset '64'"):
+        nt.decode_phred("B[N[Naaeeeae?", base_64=True)
