@@ -395,13 +395,31 @@ class Context:
         return {f: int(getattr(t, f)) for f in TALLY_FIELDS}
 
 
+def _snippet(seq, max_len=20):
+    # python.rs:37-45 get_seq_snippet
+    return seq[:max_len - 4] + "\u2026" + seq[-3:] if len(seq) > max_len else seq
+
+
 class Record:
-    """Mirrors needletail's Python Record (src/python.rs:125-264): id, seq, qual as str."""
+    """needletail's Python Record (src/python.rs:88-287): ``Record(id, seq, qual=None)`` with ``id``, ``seq``, ``qual``
+    as str, ``name`` / ``description``, ``is_fasta()`` / ``is_fastq()``, ``normalize(iupac=False)``, ``==``, ``hash``,
+    ``len``, ``str`` (the record as FASTA / FASTQ text) and ``repr``.  Records yielded by a reader additionally carry
+    the reference's Rust-side accessors: ``raw_seq`` (bytes, line breaks included), ``all``, ``num_bases`` and the
+    record's ``line`` / ``byte`` position (src/parser/record.rs:66-154)."""
 
     __slots__ = ("id", "seq", "qual", "raw_seq", "all", "num_bases", "line", "byte")
 
-    def __init__(self, data, r, fmt):
+    def __init__(self, id, seq, qual=None):
+        if qual is not None and len(qual) != len(seq):
+            raise ValueError("Sequence and quality strings must have the same length")     # python.rs:207-214
+        self.id, self.seq, self.qual = id, seq, qual
+        self.raw_seq = seq.encode()
+        self.all, self.num_bases, self.line, self.byte = None, len(seq), None, None
+
+    @classmethod
+    def _from_table(cls, data, r, fmt):
         b = data
+        self = cls.__new__(cls)
         self.id = b[r.id_b:r.id_e].tobytes().decode("utf-8", errors="replace")
         self.raw_seq = b[r.seq_b:r.seq_e].tobytes()
         # Record.seq is SequenceRecord::seq(): raw_seq minus all \r\n (src/parser/record.rs:84-89, python.rs:136-142)
@@ -411,12 +429,52 @@ class Record:
         self.num_bases = int(r.num_bases)
         self.line = int(r.line)
         self.byte = int(r.start)
+        return self
+
+    def _first_ws(self):
+        for i, c in enumerate(self.id):
+            if c.isspace():
+                return i
+        return -1
+
+    @property
+    def name(self):                                   # python.rs:148-154: the id up to its first whitespace character
+        i = self._first_ws()
+        return self.id if i < 0 else self.id[:i]
+
+    @property
+    def description(self):                            # python.rs:157-163: what follows it, left-trimmed; None without whitespace
+        i = self._first_ws()
+        return None if i < 0 else self.id[i:].lstrip()
 
     def is_fasta(self):
         return self.qual is None
 
     def is_fastq(self):
         return self.qual is not None
+
+    def normalize(self, iupac=False, ctx=None):
+        """In place, like python.rs:197-202 (the normalisation itself is ntg_normalize on the device)."""
+        self.seq = normalize_seq(self.seq, iupac, ctx)
+
+    def __eq__(self, other):
+        return isinstance(other, Record) and (self.id, self.seq, self.qual) == (other.id, other.seq, other.qual)
+
+    def __hash__(self):
+        return hash((self.id, self.seq)) if self.qual is None else hash((self.id, self.seq, self.qual))
+
+    def __len__(self):
+        return len(self.seq)
+
+    def __str__(self):
+        if self.qual is None:
+            return ">%s\n%s\n" % (self.id, self.seq)
+        return "@%s\n%s\n+\n%s\n" % (self.id, self.seq, self.qual)
+
+    def __repr__(self):
+        name = self.name
+        id_snippet = name + "\u2026" if name != self.id else name
+        return "Record(id=%s, seq=%s, qual=%s)" % (id_snippet, _snippet(self.seq), "None" if self.qual is None else _snippet(self.qual))
 
 
 class Parsed:
@@ -426,7 +484,7 @@ class Parsed:
         self.final_line, self.final_byte = int(rs.final_line), int(rs.final_byte)
         n = int(rs.n_records)
         self.table = np.ctypeslib.as_array(C.cast(rs.records, C.POINTER(C.c_uint64)), shape=(n, 10)).copy() if n else np.zeros((0, 10), np.uint64)
-        self.records = [Record(data, rs.records[i], self.format) for i in range(n)]
+        self.records = [Record._from_table(data, rs.records[i], self.format) for i in range(n)]
         e = rs.error
         self.err_kind = ERROR_KINDS.get(e.kind) if e.kind else None
         self.err_line = int(e.line)

@@ -67,6 +67,11 @@ def test_normalize_vectors_gpu(ctx):  # src/sequence.rs:316-344 ; test_python.py
 def test_python_face_vectors(ctx):  # test_python.py:101-149,171-226
     import needletail_b200 as nt
     assert nt.normalize_seq("ACGTU", iupac=False, ctx=ctx) == "ACGTT"
+    rec = nt.Record("test", "AGCTGYrtcga")                                   # test_python.py:37-42
+    rec.normalize(iupac=True, ctx=ctx)
+    assert rec.seq == "AGCTGYRTCGA"
+    rec.normalize(ctx=ctx)
+    assert rec.seq == "AGCTGNNTCGA"
     assert nt.normalize_seq("bdhvryswkm", iupac=True, ctx=ctx) == "BDHVRYSWKM"
     assert nt.reverse_complement("atcg", ctx=ctx) == "cgat"
     assert nt.reverse_complement("ATCG", ctx=ctx) == "CGAT"

@@ -143,3 +143,60 @@ def test_decode_phred_vectors():
         nt.decode_phred("#</</BBFFFBF ")
     with pytest.raises(ValueError, match=r"character '\?' cannot be decoded with offset '64'"):
         nt.decode_phred("B[N[Naaeeeae?", base_64=True)
+
+
+def test_record_class_mirrors_reference_python_module():
+    """test_python.py:17-99 (RecordClassTestCase) minus normalize(), which runs on the device (tests/test_gpu_parity.py)."""
+    from needletail_b200 import Record
+    r = Record("test description", "AGCTGATCGA")
+    assert (r.id, r.seq, r.qual) == ("test description", "AGCTGATCGA", None)
+    assert (r.name, r.description) == ("test", "description")
+    assert Record("test", "A").description is None and Record("test", "A").name == "test"
+    q = Record("test description", "AGCTGATCGA", ";**9;;????")
+    assert q.qual == ";**9;;????" and q.is_fastq() and not q.is_fasta() and r.is_fasta() and not r.is_fastq()
+    with pytest.raises(ValueError):
+        Record("x", "ACGT", "II")
+    r1, r2 = Record("test", "AGCTGATCGA", ";**9;;????"), Record("test", "AGCTGATCGA", ";**9;;????")
+    others = [Record("test2", "AGCTGATCGA", ";**9;;????"), Record("test", "TCGATCAGCT", ";**9;;????"),
+              Record("test", "AGCTGATCGA", "????;**9;;"), Record("test", "AGCTGATCGA")]
+    assert r1 == r2 and hash(r1) == hash(r2) and all(r1 != o for o in others) and all(hash(r1) != hash(o) for o in others)
+    assert str(Record("test", "AGCTGATCGA")) == ">test\nAGCTGATCGA\n"
+    assert str(Record("test", "AGCTGATCGA", ";**9;;????")) == "@test\nAGCTGATCGA\n+\n;**9;;????\n"
+    assert repr(Record("test", "AGCTGATCGAAGCTGATCGAA")) == "Record(id=test, seq=AGCTGATCGAAGCTGA\u2026GAA, qual=None)"
+    assert repr(Record("test", "AGCTGATCGAAGCTGATCGAA", ";**9;;????;**9;;????;")) == \
+        "Record(id=test, seq=AGCTGATCGAAGCTGA\u2026GAA, qual=;**9;;????;**9;;\u2026??;)"
+    assert repr(Record("test more", "ACGT")) == "Record(id=test\u2026, seq=ACGT, qual=None)"
+    assert len(Record("test", "AGCTGATCGA")) == 10
+
+
+def test_record_normalize_plumbing():
+    """Record.normalize / normalize_seq hand the bytes to Context.normalize and put the str back (test_python.py:37-42);
+    the context here is a stand-in answering with the oracle, the real device path is tests/test_gpu_parity.py."""
+    import needletail_b200 as nt
+    import oracle_lib as O
+
+    class FakeCtx:
+        def normalize(self, seqs, iupac=False):
+            res = [O.normalize(s, iupac) for s in seqs]
+            return [r[0] for r in res], [r[1] for r in res]
+
+    r = nt.Record("test", "AGCTGYrtcga")
+    r.normalize(iupac=True, ctx=FakeCtx())
+    assert r.seq == "AGCTGYRTCGA"
+    r.normalize(ctx=FakeCtx())
+    assert r.seq == "AGCTGNNTCGA"
+
+
+def test_record_from_table_row():
+    """Records yielded by a reader are cut out of the input by the ten offsets of an ntg_record row (include/ntgpu.h)."""
+    from types import SimpleNamespace
+    import needletail_b200 as nt
+    data = np.frombuffer(b"@id one\nAC\r\n+\nII\r\n>x\nAC\nGT\n", dtype=np.uint8)
+    row = SimpleNamespace(start=0, all_e=17, id_b=1, id_e=7, seq_b=8, seq_e=10, qual_b=14, qual_e=16, num_bases=2, line=1)
+    r = nt.Record._from_table(data, row, "fastq")
+    assert (r.id, r.seq, r.qual, r.raw_seq, r.num_bases, r.line, r.byte) == ("id one", "AC", "II", b"AC", 2, 1, 0)
+    assert r.all == b"@id one\nAC\r\n+\nII\r" and r.name == "id" and r.description == "one" and r.is_fastq()
+    row = SimpleNamespace(start=18, all_e=26, id_b=19, id_e=20, seq_b=21, seq_e=26, qual_b=0, qual_e=0, num_bases=4, line=5)
+    r = nt.Record._from_table(data, row, "fasta")
+    assert (r.id, r.seq, r.qual, r.raw_seq, r.num_bases) == ("x", "ACGT", None, b"AC\nGT", 4) and r.is_fasta()
+    assert str(r) == ">x\nACGT\n" and r == nt.Record("x", "ACGT")
