@@ -337,6 +337,13 @@ struct FastLuts {
     const uint32_t* rins;    // ((3 - code) << (2(K-1) - 32)) : the complement base entering the high word of R
     const uint32_t* comb;    // cls | rins in one word (walk_clean: one table look-up per base)
 };
+__host__ __device__ __forceinline__ double u64_bits_as_double(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)v);
+#else
+    double d; std::memcpy(&d, &v, sizeof d); return d;
+#endif
+}
 __host__ __device__ __forceinline__ bool lt62(uint64_t a, uint64_t b) {
 #ifdef __CUDA_ARCH__
     return __longlong_as_double((long long)a) < __longlong_as_double((long long)b);
@@ -549,6 +556,119 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     return true;
 }
 
+// The same walk with the window minima on the FP64 pipe (experiment, NTG_FP64_MIN=1; measured in round 2): the three
+// 64-bit minima per base cost the INT pipe 2 SEL each on top of the DSETP; m-mer scores are below 2^42, so they can
+// live as exact doubles, min(a,b) = a - max(a-b,0) is three exact FP64 operations, and twice the sum of the window
+// minima accumulates exactly in a double.  The canonical k-mer part stays on integers (62 bits).
+template <int K, int M>
+__host__ __device__ __forceinline__ bool walk_clean_fp(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, Acc& acc) {
+    static_assert(K >= 21 && K <= 31 && M > 0 && M <= K && 2 * M <= 42 && (K - M) >= 8 && (K - M) <= 16, "FP64-minimum clean walker shape");
+    constexpr bool MINI = M > 0;
+    constexpr int W = MINI ? K - M + 1 : 1;
+    constexpr int B = MINI ? W : 8;                  // bases per unrolled block
+    constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
+    constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
+    constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
+    constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
+    constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
+    uint64_t f = 0, r = 0, s_k = 0;
+    double pre = 0.0, s_m2 = 0.0;                    // s_m2: twice the sum of the window minima (exact: < 2^53, see the length guard)
+    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
+    double buf[W + 1];
+#pragma unroll
+    for (int i = 0; i <= W; i++) buf[i] = 0.0;
+    if (b - ws > 1000) return false;                 // 1000 * 2 * 4^M < 2^53 keeps every partial sum exact
+    int p = ws;
+
+    // Leave as soon as a lane of the (converged part of the) warp has met a byte this walker cannot handle: the warp then
+    // redoes its items with walk_fast together instead of finishing a walk whose result is thrown away.  A hint only:
+    // exactness rests on each lane's own `seen` test at the end.
+    auto bail = [&]() -> bool {
+#if defined(__CUDA_ARCH__)
+        return __any_sync(__activemask(), (seen & 0x84u) != 0u);
+#else
+        return (seen & 0x84u) != 0u;
+#endif
+    };
+    auto roll = [&](int pp) {
+        const uint32_t u = comb[sb[pp]];
+        seen |= u;
+        f = (f << 2) | (uint64_t)(u & 3u);
+        r = (r >> 2) | ((uint64_t)(u & RMASK) << 32);
+    };
+    // score of the m-mer x ending here as an exact double (x < 2^42): bit pattern 2^52 + x, minus 2^52.  RC_k(x) < x is
+    // the rare case of walk_clean (R < 4^M): remembered in rtop_min, the item then goes to walk_fast.
+    auto score = [&]() -> double {
+        const uint64_t x = f & MMASK;
+        const uint32_t top = (2 * M >= 32) ? (uint32_t)(r >> 32) : (uint32_t)(r >> (2 * M));
+        rtop_min = top < rtop_min ? top : rtop_min;
+        return u64_bits_as_double(0x4330000000000000ull | x) - 4503599627370496.0;
+    };
+    // min(a, b) of two integer-valued doubles below 2^52 with three FP64-pipe operations, all exact: a - max(a - b, 0)
+    auto dmin = [&](double a, double bb) -> double { const double t = a - bb; return fma(-0.5, t + fabs(t), a); };
+    auto tally = [&]() {
+        const uint64_t fm = f & KMASK;
+        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
+        s_k += lt ? fm : r;
+        n_nrc += lt ? 1u : 0u;
+    };
+    // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
+    auto block = [&](auto check) {
+        constexpr bool CHECK = decltype(check)::value;
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            if (CHECK && p + j >= b) return;
+            roll(p + j);
+            const double sc = score();
+            if (j == 0) {
+                pre = (W == 1) ? sc : dmin(sc, pre);
+                s_m2 = fma(2.0, pre, s_m2);
+                buf[W - 1] = sc;
+#pragma unroll
+                for (int q = W - 2; q >= 1; q--) buf[q] = dmin(buf[q], buf[q + 1]);
+            } else {
+                const int i = j - 1;
+                pre = (i == 0) ? sc : dmin(sc, pre);
+                const double u = buf[i + 1];
+                s_m2 += u + pre;                             // 2 min(u, pre) = (u + pre) - |u - pre|
+                s_m2 -= fabs(u - pre);
+                buf[i] = sc;
+            }
+            tally();
+        }
+    };
+
+    // head: K-1 bases that cannot end a k-mer — M-1 of them only feed F / R, the other W-1 are the first scores
+    {
+        const int e0 = ws + (MINI ? M - 1 : K - 1), e1 = b < e0 ? b : e0;
+#pragma unroll 4
+        for (; p < e1; p++) roll(p);
+        if (MINI) {
+#pragma unroll
+            for (int i = 0; i < W - 1; i++) {
+                if (p + i < b) {
+                    roll(p + i);
+                    const double sc = score();
+                    pre = (i == 0) ? sc : dmin(sc, pre);
+                    buf[i] = sc;
+                }
+            }
+            p += W - 1;
+        }
+    }
+    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
+    while (p + B <= b) { block(FalseT{}); p += B; if (NTG_BAIL_VOTE >= 2 && bail()) return false; }
+    if (p < b) block(TrueT{});
+    if ((seen & 0x84u) || rtop_min < RTOP_LIMIT) return false;
+    const int nk_i = b - (ws + K - 1);
+    const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
+    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
+    acc.ksum_lo += s_k;
+    acc.n_mini += nk; acc.msum += (uint64_t)(s_m2 * 0.5);
+    return true;
+}
+
+
 // =============================================================================== look-back
 __device__ __forceinline__ SState shfl_state(const SState& v, int src) {
     SState r;
@@ -689,6 +809,9 @@ __device__ __noinline__ void walk_slow(const uint8_t* sb, const uint8_t* lut, in
 #ifndef NTG_LB_WIDE
 #define NTG_LB_WIDE 0                                // 1: warp_lookback_wide (window 32 * NTGPU_LB_G tiles) instead of the 32-tile look-back.
 #endif                                               //    Measured slower (B200, C2: G=1 396, G=2 401-410, G=10 330 vs 425 Gbases/s): kept for A/B only
+#ifndef NTG_FP64_MIN
+#define NTG_FP64_MIN 0                               // 1: walk_clean_fp (window minima on the FP64 pipe) for the shapes it covers
+#endif
 #ifndef NTG_CLEAN
 #define NTG_CLEAN 1                                  // 0: items go straight to walk_fast (the round-1 kernel), for A/B timing
 #endif
@@ -715,7 +838,11 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
         constexpr int CK = FK > 0 ? FK : 21, CM = FK > 0 ? FM : 0;
         bool done = false;
         if (NTG_CLEAN && CK >= 21) {
-            if (!__any_sync(__activemask(), mode != 0u)) done = walk_clean<(CK >= 21 ? CK : 21), (CK >= 21 ? CM : 0)>(sb, comb, ws, b, acc);
+            if (!__any_sync(__activemask(), mode != 0u)) {
+                constexpr bool FP = NTG_FP64_MIN && CM > 0 && 2 * CM <= 42 && CK - CM >= 8 && CK - CM <= 16;
+                if (FP) done = walk_clean_fp<(FP ? CK : 31), (FP ? CM : 21)>(sb, comb, ws, b, acc);
+                else done = walk_clean<(CK >= 21 ? CK : 21), (CK >= 21 ? CM : 0)>(sb, comb, ws, b, acc);
+            }
             if (!done) {
                 uint32_t seen = 0x80u;
                 done = walk_fast_cold<CK, CM>(sb, lut, rins, ws, b, acc, &seen);
@@ -770,6 +897,9 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
 }
 
 
+#ifndef NTG_TICKET
+#define NTG_TICKET 0                                 // 1: tiles are handed out by an atomic ticket instead of round-robin (A/B experiment)
+#endif
 #ifndef NTG_LB_DEFER
 #define NTG_LB_DEFER 1                               // 0: every tile's look-back is resolved inside its own tile (round-1 behaviour), for A/B timing
 #endif
@@ -865,7 +995,15 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         // Static round-robin tile assignment: CTA b takes tiles b, b + grid, b + 2 grid, ...  (No ticket: a tile that is
         // claimed early but processed late publishes its aggregate late and stalls every look-back behind it; with the
         // static order the next tile is known in advance, so it can be prefetched into L2 without being "claimed".)
+#if NTG_TICKET
+        // (experiment) dynamic order: the next unclaimed tile.  With the aggregate published early in the tile and the look-back
+        // deferred, a late claimer hurts less than in round 1, and SMs that run faster take more tiles instead of waiting.
+        if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
+        __syncthreads();
+        chunk_first = tile_begin + (uint64_t)S.tile_idx;
+#else
         chunk_first = tile_begin + (uint64_t)blockIdx.x + (uint64_t)my_seq * gridDim.x;
+#endif
         in_chunk = 0;
         const uint64_t t = chunk_first + in_chunk;
         if (t >= tile_end) break;
@@ -999,7 +1137,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             if (lane == 0) {
                 // next tile of this CTA: pull it into L2 while the walkers work on this one
                 const uint64_t tn = t + gridDim.x;
-                if (tn < tile_end) {
+                if (!NTG_TICKET && tn < tile_end) {
                     const uint64_t ns = tn * (uint64_t)TB;
                     const uint32_t nbytes = (uint32_t)min((uint64_t)TB, P.n - ns) & ~15u;
                     if (nbytes) bulk_prefetch_l2(P.bytes + ns, nbytes);
