@@ -567,9 +567,8 @@ __host__ __device__ __forceinline__ bool walk_clean_fp(const uint8_t* __restrict
     constexpr int W = MINI ? K - M + 1 : 1;
     constexpr int B = MINI ? W : 8;                  // bases per unrolled block
     constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
-    constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
+    constexpr uint64_t MMASK = (1ull << (2 * M)) - 1;
     constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
-    constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
     constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
     uint64_t f = 0, r = 0, s_k = 0;
     double pre = 0.0, s_m2 = 0.0;                    // s_m2: twice the sum of the window minima (exact: < 2^53, see the length guard)
