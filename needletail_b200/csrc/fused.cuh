@@ -896,6 +896,10 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
 }
 
 
+#ifndef NTG_STATS
+#define NTG_STATS 0                                  // 1: per-CTA cycle accounting into tallies[9..15] (ntg_tallies.reserved[2..6]):
+#endif                                               //    [9] sum of CTA lifetimes, [10] coordinator cycles inside look-backs, [11] look-backs,
+                                                     //    [12] longest CTA lifetime, [14] thread 0 at the end-of-walk barrier, [15] thread 0 walking
 #ifndef NTG_TICKET
 #define NTG_TICKET 0                                 // 1: tiles are handed out by an atomic ticket instead of round-robin (A/B experiment)
 #endif
@@ -981,6 +985,10 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0; }
     __syncthreads();
     uint32_t parity = 0, slow = 0, my_seq = 0, mode = 0;
+#if NTG_STATS
+    const long long st_t0 = clock64();
+    long long st_lb = 0, st_wait = 0, st_walk = 0, st_mark = 0; uint32_t st_nlb = 0;
+#endif
     Acc acc;
     const uint8_t* sb = S.tile;
     const bool fasta = P.format == NTG_FMT_FASTA;
@@ -1110,7 +1118,15 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 st_release_u32(&slot->flag, epoch * 4 + 1);
             }
             __syncwarp();
-            if (S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);
+#if NTG_STATS
+            st_mark = clock64();
+#endif
+            if (S.pend_valid) {
+                resolve_pending(P, S, epoch, lane, acc, slow);
+#if NTG_STATS
+                st_nlb++;
+#endif
+            }
             if (defer) {
                 if (lane == 0) {
                     S.pend_agg = agg; S.pend_t = t; S.pend_guess = guess; S.pend_cs = Cs; S.pend_avail = avail;
@@ -1133,6 +1149,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                     S.prefix_seq = my_seq + 1;
                 }
             }
+#if NTG_STATS
+            st_lb += clock64() - st_mark; if (!defer && t > 0) st_nlb++;
+#endif
             if (lane == 0) {
                 // next tile of this CTA: pull it into L2 while the walkers work on this one
                 const uint64_t tn = t + gridDim.x;
@@ -1224,6 +1243,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             else if (is_coord && have_pre) { for (uint32_t i = lane; i <= Cs && i < 4; i += 32) line_events(i); }   // (deferred: resolve_pending)
             // (B) sequence lines only: walker thread j takes the j-th role-1 line of the tile (every 4th line)
             const uint32_t i_first = (1u - ord0) & 3u;
+#if NTG_STATS
+            st_mark = clock64();
+#endif
             if (!is_coord) {
                 for (uint32_t i = i_first + 4u * tid; i <= Cs + 1; i += 4u * NTW) {
                     if (spec) {                                             // events of this record's lines (header .. quality)
@@ -1273,7 +1295,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, true, slow, mode);
             }
         }
+#if NTG_STATS
+        const long long st_done = clock64();
+#endif
         __syncthreads();
+#if NTG_STATS
+        if (!fasta && !is_coord) { st_walk += st_done - st_mark; st_wait += clock64() - st_done; }
+#endif
         // ---- long lines: SEG-byte pieces shared by the whole CTA
         const uint32_t n_long = min(S.n_long, (uint32_t)LONGMAX);
         // piece length: about one piece per thread when the tile is made of long lines (at least 128 B, at most SEG)
@@ -1307,6 +1335,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 
     if (is_coord && S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);      // the last deferred tile of this CTA
 
+#if NTG_STATS
+    {
+        const unsigned long long life = (unsigned long long)(clock64() - st_t0);
+        if (tid == 0) { atomicAdd(&P.tallies[9], life); atomicMax(&P.tallies[12], life);
+                        atomicAdd(&P.tallies[14], (unsigned long long)st_wait); atomicAdd(&P.tallies[15], (unsigned long long)st_walk); }
+        if (tid == NTW) { atomicAdd(&P.tallies[10], (unsigned long long)st_lb); atomicAdd(&P.tallies[11], (unsigned long long)st_nlb); }
+    }
+#endif
     // ---- P4: block reduction of the register tallies, 9 atomics per CTA
     uint64_t v[9] = {acc.n_records, acc.n_bases, acc.n_kmers, acc.n_not_rc, acc.ksum_lo, acc.ksum_hi, acc.n_query, acc.n_mini, acc.msum};
 #pragma unroll
