@@ -12,6 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run under gpurun)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build the product library once if it is MISSING
+    (same recipe as __graft_entry__.build(); an existing library is never rebuilt here — on the GPU box the one that
+    travelled with the snapshot is what must be tested)."""
+    so = os.environ.get("NTGPU_SO", os.path.join(ROOT, "needletail_b200", "libntgpu.so"))
+    if not os.path.exists(so) and "NTGPU_SO" not in os.environ:
+        from needletail_b200 import build as nt_build
+        nt_build.build()
+
+
 _FIXTURES = None
 
 
