@@ -906,6 +906,52 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
 #ifndef NTG_LB_DEFER
 #define NTG_LB_DEFER 1                               // 0: every tile's look-back is resolved inside its own tile (round-1 behaviour), for A/B timing
 #endif
+// Line events (fastq.rs:240-285) of line i < 4 of a tile, from global memory: start byte ('@' at role 0, '+' at role 2),
+// n_bases of a sequence line and the length check / n_records of a quality line that END in the tile.  `nl4` = the tile's
+// first four newline offsets (tile-relative), Cs = number of newlines in the tile, `pre` = the tile's exclusive prefix
+// (line roles come from its newline count, lines that began in earlier tiles from its last[] positions).  i <= Cs.
+// __host__ __device__: tests/cpp/test_walkers.cu checks it against a direct evaluation of the definition.
+__host__ __device__ __forceinline__ void first_lines_event(const uint8_t* __restrict__ bytes, uint64_t tile_start, const uint32_t* nl4, uint32_t Cs,
+                                                           uint32_t avail, bool line0_starts_here, const SState& pre, uint32_t i, Acc& acc,
+                                                           uint32_t& slow) {
+    const uint32_t ord0 = (uint32_t)(pre.count & 3);
+    auto nl = [&](uint32_t j) -> uint64_t { return tile_start + nl4[j]; };                        // j < min(Cs, 4)
+    auto prev_nl = [&](uint32_t back) -> uint64_t {                                               // `back` newlines before newline i
+        if (i >= back) return nl(i - back);
+        const uint32_t r = back - i - 1;
+        return r < 4 ? pre.last[r] : NONE;
+    };
+    auto cr_before = [&](uint64_t q, uint64_t prevq) -> uint32_t {                                // trim_cr on the line (prevq, q)
+        const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
+        return (q > ls && bytes[q - 1] == '\r') ? 1u : 0u;
+    };
+    const uint32_t role = (ord0 + i) & 3;
+    const uint64_t s = i ? nl(i - 1) + 1 : tile_start;
+    const bool starts = (i > 0 || line0_starts_here) && (s - tile_start) < avail;
+    if (starts) {
+        const uint8_t c = bytes[s];
+        if (role == 0 && c != '@') slow |= FLAG_PARSE_ERROR;
+        if (role == 2 && c != '+') slow |= FLAG_PARSE_ERROR;
+    }
+    if (i < Cs) {
+        const uint64_t q = nl(i);
+        if (role == 1) {
+            const uint64_t p1 = prev_nl(1);
+            const uint64_t ls = p1 == NONE ? 0 : p1 + 1;
+            acc.n_bases += (q - ls) - cr_before(q, p1);
+        } else if (role == 3) {
+            const uint64_t q2 = prev_nl(1), q1 = prev_nl(2), q0 = prev_nl(3);
+            if (q2 == NONE || q1 == NONE || q0 == NONE) slow |= FLAG_PARSE_ERROR;
+            else {
+                const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
+                const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
+                if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;
+                acc.n_records++;
+            }
+        }
+    }
+}
+
 // Coordinator warp: resolve the tile deferred at the previous P2c — look-back, inclusive prefix, check of the speculated
 // line phase, and the line events (fastq.rs:240-285) of the tile's first four lines, the ones that may need the prefix.
 // The tile's bytes have left shared memory by now: the few bytes involved are read from global memory (L2).
@@ -924,45 +970,9 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
     }
     const uint32_t ord0 = (uint32_t)(pre.count & 3);
     if (S.pend_guess != ord0) slow |= FLAG_SPEC_MISS;
-    const uint32_t Cs = S.pend_cs, avail = S.pend_avail, i = lane;
-    const uint64_t tile_start = t * (uint64_t)P.tile_bytes;
-    if (i < 4 && i <= Cs) {
-        auto nl = [&](uint32_t j) -> uint64_t { return tile_start + S.pend_nl4[j]; };                 // j < min(Cs, 4)
-        auto prev_nl = [&](uint32_t back) -> uint64_t {                                               // `back` newlines before newline i
-            if (i >= back) return nl(i - back);
-            const uint32_t r = back - i - 1;
-            return r < 4 ? pre.last[r] : NONE;
-        };
-        auto cr_before = [&](uint64_t q, uint64_t prevq) -> uint32_t {                                // trim_cr on the line (prevq, q)
-            const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
-            return (q > ls && P.bytes[q - 1] == '\r') ? 1u : 0u;
-        };
-        const uint32_t role = (ord0 + i) & 3;
-        const uint64_t s = i ? nl(i - 1) + 1 : tile_start;
-        const bool starts = (i > 0 || S.pend_line0 != 0) && (s - tile_start) < avail;
-        if (starts) {
-            const uint8_t c = P.bytes[s];
-            if (role == 0 && c != '@') slow |= FLAG_PARSE_ERROR;
-            if (role == 2 && c != '+') slow |= FLAG_PARSE_ERROR;
-        }
-        if (i < Cs) {
-            const uint64_t q = nl(i);
-            if (role == 1) {
-                const uint64_t p1 = prev_nl(1);
-                const uint64_t ls = p1 == NONE ? 0 : p1 + 1;
-                acc.n_bases += (q - ls) - cr_before(q, p1);
-            } else if (role == 3) {
-                const uint64_t q2 = prev_nl(1), q1 = prev_nl(2), q0 = prev_nl(3);
-                if (q2 == NONE || q1 == NONE || q0 == NONE) slow |= FLAG_PARSE_ERROR;
-                else {
-                    const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
-                    const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
-                    if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;
-                    acc.n_records++;
-                }
-            }
-        }
-    }
+    const uint32_t Cs = S.pend_cs;
+    if (lane < 4 && lane <= Cs)
+        first_lines_event(P.bytes, t * (uint64_t)P.tile_bytes, S.pend_nl4, Cs, S.pend_avail, S.pend_line0 != 0, pre, lane, acc, slow);
     __syncwarp();
     if (lane == 0) S.pend_valid = 0;
     __syncwarp();

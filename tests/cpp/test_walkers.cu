@@ -1,4 +1,5 @@
-// Host-side differential test of the fused kernel's row scanner (scan_row) and per-item walkers
+// Host-side differential test of the fused kernel's row scanner (scan_row), the deferred first-lines events
+// (first_lines_event) and the per-item walkers
 // (needletail_b200/csrc/fused.cuh: find_ws, walk, walk_fast, walk_clean) against the oracle's tally_sequence (oracle/ntref.hpp).  The walkers are __host__ __device__:
 // this file compiles the very same source for the CPU (no device code is launched) and checks, on random lines,
 //   1. every walker that accepts an item returns exactly the oracle's tallies for it,
@@ -8,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <random>
 #include <string>
 #include <vector>
@@ -138,10 +140,82 @@ static int test_scan_row(std::mt19937_64& rng) {
     return fails;
 }
 
+// first_lines_event: the line events of a tile's first four lines, evaluated by the deferred look-back from global memory
+static int test_first_lines_event(std::mt19937_64& rng) {
+    using fused::SState; using fused::NONE;
+    int fails = 0; long n_err = 0, n_rec = 0;
+    for (int it = 0; it < 30000 && fails < 5; it++) {
+        // a FASTQ-like text: mostly valid records, sometimes CRLF, sometimes damaged
+        std::string s;
+        const int nrec = 1 + (int)(rng() % 6);
+        const bool crlf = rng() % 4 == 0;
+        for (int r = 0; r < nrec; r++) {
+            const int L = (int)(rng() % 12);
+            std::string seq(L, 'A'), qual(L, 'I');
+            for (auto& c : seq) c = "ACGT"[rng() & 3];
+            for (auto& c : qual) c = "!+@I5"[rng() % 5];
+            if (rng() % 12 == 0) qual += 'I';                                  // unequal lengths
+            const char h = rng() % 15 == 0 ? 'x' : '@', p = rng() % 15 == 0 ? '-' : '+';
+            const std::string eol = crlf && rng() % 8 ? "\r\n" : "\n";
+            s += std::string(1, h) + "r" + eol + seq + eol + std::string(1, p) + eol + qual + eol;
+        }
+        if (rng() % 5 == 0 && !s.empty()) s.pop_back();                        // no final newline
+        const uint64_t n = s.size();
+        const uint8_t* bytes = (const uint8_t*)s.data();
+        std::vector<uint64_t> gnl;                                             // all newline positions
+        for (uint64_t q = 0; q < n; q++) if (bytes[q] == '\n') gnl.push_back(q);
+        const uint64_t tile_start = rng() % n;
+        const uint32_t TB = 8 + (uint32_t)(rng() % 200);
+        const uint32_t avail = (uint32_t)std::min<uint64_t>(TB, n - tile_start);
+        SState pre = fused::identity_state();
+        size_t g0 = 0;                                                         // index of the tile's first newline in gnl
+        while (g0 < gnl.size() && gnl[g0] < tile_start) g0++;
+        pre.count = g0;
+        for (int j = 0; j < 4 && j < (int)g0; j++) pre.last[j] = gnl[g0 - 1 - j];
+        uint32_t Cs = 0, nl4[4] = {0, 0, 0, 0};
+        for (size_t g = g0; g < gnl.size() && gnl[g] < tile_start + avail; g++) { if (Cs < 4) nl4[Cs] = (uint32_t)(gnl[g] - tile_start); Cs++; }
+        const bool line0 = tile_start == 0 || bytes[tile_start - 1] == '\n';
+        Acc got; uint32_t slow = 0;
+        for (uint32_t i = 0; i < 4 && i <= Cs; i++) fused::first_lines_event(bytes, tile_start, nl4, Cs, avail, line0, pre, i, got, slow);
+        // the definition, on global line ordinals
+        uint64_t want_bases = 0, want_rec = 0; bool want_err = false;
+        auto line_len = [&](uint64_t ls, uint64_t q) { return (q - ls) - ((q > ls && bytes[q - 1] == '\r') ? 1 : 0); };
+        for (uint32_t i = 0; i < 4 && i <= Cs; i++) {
+            const size_t g = g0 + i;                                           // global ordinal of this line
+            const uint32_t role = (uint32_t)(g & 3);
+            const uint64_t ls = g ? gnl[g - 1] + 1 : 0;                        // global start of the line
+            const bool starts_in_tile = ls >= tile_start && ls - tile_start < avail;
+            if (starts_in_tile && ((role == 0 && bytes[ls] != '@') || (role == 2 && bytes[ls] != '+'))) want_err = true;
+            if (i < Cs) {
+                const uint64_t q = gnl[g];
+                if (role == 1) want_bases += line_len(ls, q);
+                else if (role == 3) {
+                    if (g < 3) want_err = true;
+                    else {
+                        const uint64_t q0 = gnl[g - 3], q1 = gnl[g - 2], q2 = gnl[g - 1];
+                        if (line_len(q0 + 1, q1) != line_len(q2 + 1, q)) want_err = true;
+                        want_rec++;
+                    }
+                }
+            }
+        }
+        const bool got_err = (slow & fused::FLAG_PARSE_ERROR) != 0;
+        n_err += want_err; n_rec += (long)want_rec;
+        if (got.n_bases != want_bases || got.n_records != want_rec || got_err != want_err) {
+            std::printf("first_lines_event: tile [%llu,+%u) Cs %u: bases %llu/%llu records %llu/%llu err %d/%d\n", (unsigned long long)tile_start, avail, Cs,
+                        (unsigned long long)got.n_bases, (unsigned long long)want_bases, (unsigned long long)got.n_records, (unsigned long long)want_rec, got_err, want_err);
+            fails++;
+        }
+    }
+    std::printf("first_lines_event: %ld records completed, %ld tiles with an error; %s\n", n_rec, n_err, fails ? "FAIL" : "ok");
+    return fails;
+}
+
 int main() {
     build_cls();
     std::mt19937_64 rng(20240917);
     int fails = test_scan_row(rng);
+    fails += test_first_lines_event(rng);
     fails += run<31, 21>(rng, 6000, "k31 m21");
     fails += run<21, 11>(rng, 6000, "k21 m11");
     fails += run<31, 0>(rng, 6000, "k31 m0");
