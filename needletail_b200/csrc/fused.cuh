@@ -7,15 +7,17 @@
 // Persistent CTAs (9 walker warps + 1 coordinator warp, 2 per SM) take tiles of <= 84 KiB round-robin.  Per tile:
 //   P0  the tile (+128 B back halo) is brought into shared memory by one cp.async.bulk (TMA 1-D
 //       bulk copy, SASS UBLKCP) completing on an mbarrier; the coordinator prefetches the next tile into L2;
-//   P1  every walker thread scans 256 B rows for '\n' with 32-bit SIMD-in-register tests (rotated
-//       word order => bank-conflict free);
+//   P1  every walker thread scans 256 B rows for '\n' (scan_row: 16 x LDS.128 per row in a rotated, bank-conflict
+//       free order, branch-free SIMD-in-register byte test);
 //   P2  block scan -> sorted newline list; the coordinator warp publishes the tile's aggregate (newline
 //       count, last four newline positions, FASTA header state) and obtains the global prefix by
-//       decoupled look-back, 32 predecessors per step (single pass: the input is read from HBM once);
+//       decoupled look-back, 32 predecessors per step (single pass: the input is read from HBM once).  For
+//       speculative FASTQ tiles the look-back is deferred by one tile (resolve_pending);
 //   P3  line roles (FASTQ: newline ordinal mod 4 — walkers start on a locally inferred phase that the
 //       coordinator verifies; FASTA: '>' at line start) -> validation events, n_records / n_bases, and one
 //       sequential "walker" per sequence-line fragment: 2-bit rolling forward / reverse-complement words,
-//       canonical select, sliding-window (van Herk) minimizer;
+//       canonical select, sliding-window (van Herk) minimizer.  walk_clean takes all-ACGT items, walk_fast items
+//       with other bases, walk anything else;
 //   P4  per-thread tallies stay in registers across tiles; one block reduction + 9 atomics per CTA.
 // Anything the fast path cannot prove clean (parse error, > NLMAX newlines in a tile, whitespace
 // runs longer than the halo) raises a flag and the host re-runs the exact materialising path.
