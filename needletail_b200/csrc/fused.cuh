@@ -38,6 +38,11 @@ constexpr int SEG = 512;                 // long lines are cut into SEG-byte pie
 constexpr int CHUNK = 1;                 // tiles claimed per ticket. (>1 chains prefixes inside a CTA but serialises chunks:
                                          // a chunk's first tile then waits for the LAST tile of the previous chunk - measured 3700x slower)
 constexpr int LONGMAX = TILE / SEG + 2;
+#ifndef NTG_DC
+#define NTG_DC 0                         // 1: decoupled coordinator (experiment): the coordinator warp leaves the CTA barriers and trails the
+#endif                                   //    walkers through a small ring of per-tile records; walker thread 0 publishes the aggregates
+constexpr int NWK = NTG_DC ? NTW : NT;   // threads that run the tile loop's cooperative phases
+constexpr int DC_R = 8;                  // ring depth of the decoupled coordinator
 constexpr int LB_GMAX = 12;              // look-back: at most this many tiles per lane and step (one step spans <= 384 tiles)
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
@@ -164,6 +169,16 @@ struct __align__(16) Smem {
     uint32_t pend_guess, pend_cs, pend_avail, pend_line0;
     uint32_t pend_nl4[4];              // the tile's first four newline offsets
     volatile uint32_t pend_valid;
+#if NTG_DC
+    struct DcRec {                     // what the decoupled coordinator needs of a tile once the tile has left shared memory
+        SState agg, prefix;
+        uint64_t t;
+        uint32_t guess, cs, avail, line0, need_prefix;
+        uint32_t nl4[4];
+        volatile uint32_t prefix_ready;    // seq + 1 once `prefix` is valid (tiles whose walkers wait for it)
+    } dc[DC_R];
+    volatile uint32_t dc_head, dc_tail, dc_total;   // records produced / consumed; number of tiles of this CTA (0xffffffff until known)
+#endif
     uint32_t tile_idx;
     uint32_t tile_idx_next;            // ticket of the next tile, claimed by the coordinator during this one
     uint32_t n_long;
@@ -172,31 +187,39 @@ struct __align__(16) Smem {
     int32_t bcast[4];
 };
 
+// barrier of the threads that run the tile loop (all of the CTA, or the walkers only when the coordinator is decoupled)
+__device__ __forceinline__ void tile_sync() {
+#if NTG_DC
+    asm volatile("bar.sync 1, %0;" ::"n"(NTW) : "memory");
+#else
+    __syncthreads();
+#endif
+}
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* tmp) {
-    constexpr int NW = NT / 32;
+    constexpr int NW = NWK / 32;
     uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
     if (lane == 31) tmp[w] = inc;
-    __syncthreads();
+    tile_sync();
     if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NW; i++) { uint32_t t = tmp[i]; tmp[i] = s; s += t; } tmp[NW] = s; }
-    __syncthreads();
+    tile_sync();
     uint32_t r = inc - v + tmp[w];
     *total = tmp[NW];
-    __syncthreads();
+    tile_sync();
     return r;
 }
 __device__ __forceinline__ uint32_t block_incl_max(uint32_t v, uint32_t* tmp) {   // inclusive max-scan across threads
-    constexpr int NW = NT / 32;
+    constexpr int NW = NWK / 32;
     uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, t); }
     if (lane == 31) tmp[w] = inc;
-    __syncthreads();
+    tile_sync();
     if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NW; i++) { uint32_t t = tmp[i]; tmp[i] = s; s = max(s, t); } }
-    __syncthreads();
+    tile_sync();
     uint32_t r = max(inc, tmp[w]);
-    __syncthreads();
+    tile_sync();
     return r;
 }
 
@@ -980,6 +1003,46 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
     __syncwarp();
 }
 
+
+#if NTG_DC
+// Decoupled coordinator (experiment NTG_DC=1): consumes the per-tile records the walkers produce — look-back, inclusive
+// prefix, and either the prefix for walkers that wait for it or the check of the speculated phase plus the first four
+// lines' events (from global memory) — without ever joining a CTA barrier inside the tile loop.
+__device__ __noinline__ void dc_coordinator(const Params& P, Smem& S, uint32_t epoch, uint32_t lane, Acc& acc, uint32_t& slow) {
+    for (uint32_t seq = 0;; seq++) {
+        for (;;) {
+            if (S.dc_head > seq) break;
+            if (S.dc_total == seq) return;
+            __nanosleep(64);
+        }
+        __threadfence_block();
+        Smem::DcRec& rec = S.dc[seq % DC_R];
+        const uint64_t t = rec.t;
+        const SState agg = rec.agg;
+        SState pre = identity_state();
+        if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
+        if (lane == 0) {
+            const SState inc = combine(pre, agg);
+            TileSlot* slot = &P.slots[t];
+            slot->inc = inc;
+            __threadfence();
+            st_release_u32(&slot->flag, epoch * 4 + 2);
+            if (t + 1 == P.num_tiles) *P.final_state = inc;
+        }
+        if (rec.need_prefix) {
+            if (lane == 0) { rec.prefix = pre; __threadfence_block(); rec.prefix_ready = seq + 1; }
+        } else {
+            if (rec.guess != (uint32_t)(pre.count & 3)) slow |= FLAG_SPEC_MISS;
+            const uint32_t Cs = rec.cs;
+            if (lane < 4 && lane <= Cs)
+                first_lines_event(P.bytes, t * (uint64_t)P.tile_bytes, rec.nl4, Cs, rec.avail, rec.line0 != 0, pre, lane, acc, slow);
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); S.dc_tail = seq + 1; }
+    }
+}
+#endif
+
 template <int KW, bool MINI, int W, int FK, int FM>
 __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
@@ -994,7 +1057,12 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         S.rins[i] = ri;
         S.comb[i] = ri | c;
     }
-    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0; }
+    if (tid == 0) {
+        mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0;
+#if NTG_DC
+        S.dc_head = 0; S.dc_tail = 0; S.dc_total = 0xffffffffu;
+#endif
+    }
     __syncthreads();
     uint32_t parity = 0, slow = 0, my_seq = 0, mode = 0;
 #if NTG_STATS
@@ -1010,6 +1078,10 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 
     uint32_t in_chunk = CHUNK;                     // position inside the claimed chunk (CHUNK = claim a new one)
     uint64_t chunk_first = 0;
+#if NTG_DC
+    if (is_coord) dc_coordinator(P, S, epoch, lane, acc, slow);
+    else
+#endif
     for (;;) {
         // Static round-robin tile assignment: CTA b takes tiles b, b + grid, b + 2 grid, ...  (No ticket: a tile that is
         // claimed early but processed late publishes its aggregate late and stalls every look-back behind it; with the
@@ -1018,7 +1090,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         // (experiment) dynamic order: the next unclaimed tile.  With the aggregate published early in the tile and the look-back
         // deferred, a late claimer hurts less than in round 1, and SMs that run faster take more tiles instead of waiting.
         if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
-        __syncthreads();
+        tile_sync();
         chunk_first = tile_begin + (uint64_t)S.tile_idx;
 #else
         chunk_first = tile_begin + (uint64_t)blockIdx.x + (uint64_t)my_seq * gridDim.x;
@@ -1034,16 +1106,19 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         const uint32_t halo = t > 0 ? HALO : 0;
         const uint32_t bulk = avail & ~15u;
 
+#if NTG_DC
+        if (tid == 0) while (my_seq - S.dc_tail >= (uint32_t)DC_R) __nanosleep(64);      // ring full: the coordinator is DC_R tiles behind
+#endif
         if (tid == 0) S.n_long = 0;
         // ---- P0: stage the tile (+ back halo) with one bulk async copy
         if (tid == 0 && halo + bulk) {
             mbar_expect_tx(&S.bar, halo + bulk);
             bulk_g2s(S.halo + (HALO - halo), P.bytes + tile_start - halo, halo + bulk, &S.bar);
         }
-        if (avail < TB) for (uint32_t i = bulk + tid; i < TB; i += NT) S.tile[i] = i < avail ? P.bytes[tile_start + i] : 0;
-        if (t == 0) for (int i = tid; i < HALO; i += NT) S.halo[i] = 0;
+        if (avail < TB) for (uint32_t i = bulk + tid; i < TB; i += NWK) S.tile[i] = i < avail ? P.bytes[tile_start + i] : 0;
+        if (t == 0) for (int i = tid; i < HALO; i += NWK) S.halo[i] = 0;
         if (halo + bulk) { mbar_wait(&S.bar, parity); parity ^= 1; }
-        __syncthreads();
+        tile_sync();
 
         // ---- P1: newline scan, 256 B rows, row = round * NT + tid (rotated word order: conflict-free LDS.32)
         const uint32_t nrows = TB / ROWB;
@@ -1080,7 +1155,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 }
             }
         }
-        __syncthreads();
+        tile_sync();
         const uint32_t Cs = overflow ? 0 : C;                          // lines are only interpreted when the list is complete
         // line i (0..Cs) spans (nl[i-1], nl[i]) ; helpers on tile-relative coordinates
         auto line_start_rel = [&](uint32_t i) -> int { return i ? (int)S.nl[i - 1] + 1 : 0; };   // for i == 0: start of the in-tile fragment
@@ -1090,7 +1165,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         // ---- P2b: FASTA start events that do not need the prefix
         uint32_t my_last_start = 0, my_nstarts = 0;                    // (line index + 1) of the last start seen by this thread
         if (fasta) {
-            for (uint32_t i = tid; i <= Cs; i += NT) {
+            for (uint32_t i = tid; i <= Cs; i += NWK) {
                 const int s = line_start_rel(i);
                 const bool starts = (i > 0 || line0_starts_here) && (uint32_t)s < avail;
                 if (starts && sb[s] == '>') { my_last_start = i + 1; my_nstarts++; }
@@ -1100,8 +1175,8 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         if (fasta) {
             last_start1 = block_incl_max(my_last_start, S.warp_tmp);
             uint32_t tot; block_excl_scan(my_nstarts, &tot, S.warp_tmp); nstarts_tot = tot;
-            if (tid == NT - 1) S.bcast[0] = (int32_t)last_start1;
-            __syncthreads();
+            if (tid == NWK - 1) S.bcast[0] = (int32_t)last_start1;
+            tile_sync();
             last_start1 = (uint32_t)S.bcast[0];
         }
 
@@ -1112,7 +1187,39 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         // skew between CTAs, and the end-of-tile barrier no longer waits for a look-back that has just begun), verifies
         // that tile's guess and does the events of its first four lines from global memory.
         const uint32_t guess = spec ? guess_phase(S.nl, sb, Cs, avail, line0_starts_here) : 4u;
-        const bool defer = NTG_LB_DEFER && spec && guess != 4u && t > 0;      // (tile 0 has nothing to look back at)
+        const bool defer = !NTG_DC && NTG_LB_DEFER && spec && guess != 4u && t > 0;      // (tile 0 has nothing to look back at)
+#if NTG_DC
+        // Decoupled coordinator: walker thread 0 publishes the aggregate and hands the tile's record to the coordinator's ring.
+        const bool need_prefix = !spec || guess == 4u;            // the walkers of this tile wait for its prefix
+        if (tid == 0) {
+            SState agg = identity_state();
+            agg.count = C;
+            if (!overflow) for (uint32_t j = 0; j < 4 && j < C; j++) agg.last[j] = tile_start + S.nl[C - 1 - j];
+            if (fasta) {
+                agg.n_starts = nstarts_tot;
+                agg.first_nl = Cs ? tile_start + S.nl[0] : NONE;
+                if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
+            }
+            if (t > 0) {
+                TileSlot* slot = &P.slots[t];
+                slot->agg = agg;
+                __threadfence();
+                st_release_u32(&slot->flag, epoch * 4 + 1);
+            }
+            Smem::DcRec& rec = S.dc[my_seq % DC_R];
+            rec.agg = agg; rec.t = t; rec.guess = guess; rec.cs = Cs; rec.avail = avail; rec.line0 = line0_starts_here ? 1u : 0u;
+            rec.need_prefix = need_prefix ? 1u : 0u;
+            for (uint32_t j = 0; j < 4; j++) rec.nl4[j] = j < Cs ? S.nl[j] : 0u;
+            __threadfence_block();
+            S.dc_head = my_seq + 1;
+            const uint64_t tn = t + gridDim.x;                    // next tile of this CTA: pull it into L2
+            if (!NTG_TICKET && tn < tile_end) {
+                const uint64_t ns = tn * (uint64_t)TB;
+                const uint32_t nbytes = (uint32_t)min((uint64_t)TB, P.n - ns) & ~15u;
+                if (nbytes) bulk_prefetch_l2(P.bytes + ns, nbytes);
+            }
+        }
+#endif
         SState pre = identity_state();
         if (is_coord) {
             SState agg = identity_state();
@@ -1176,7 +1283,16 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             __syncwarp();
         }
         bool have_pre = is_coord && !defer;
-        if (!spec) { __syncthreads(); pre = S.prefix; have_pre = true; }      // everyone needs the prefix before going on
+#if NTG_DC
+        if (need_prefix) {                                        // FASTA / no unique local phase: wait for the coordinator
+            const Smem::DcRec& rec = S.dc[my_seq % DC_R];
+            while (rec.prefix_ready != my_seq + 1) __nanosleep(32);
+            __threadfence_block();
+            pre = rec.prefix; have_pre = true;
+        }
+#else
+        if (!spec) { tile_sync(); pre = S.prefix; have_pre = true; }      // everyone needs the prefix before going on
+#endif
         // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
         auto prev_nl = [&](uint32_t i, uint32_t back) -> uint64_t {
             if (i >= back) return tile_start + S.nl[i - back];
@@ -1251,8 +1367,11 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             // Without speculation every thread has the prefix and takes lines tid, tid+NT, ...  With speculation the
             // coordinator warp (which has the prefix) takes the lines that may need it — the first four of the tile —
             // and each walker takes the lines >= 4 of "its" record, whose previous newlines are all in the tile's list.
-            if (!spec) { for (uint32_t i = tid; i <= Cs; i += NT) line_events(i); }
+            if (!spec) { for (uint32_t i = tid; i <= Cs; i += NWK) line_events(i); }
             else if (is_coord && have_pre) { for (uint32_t i = lane; i <= Cs && i < 4; i += 32) line_events(i); }   // (deferred: resolve_pending)
+#if NTG_DC
+            else if (have_pre && tid < 4 && (uint32_t)tid <= Cs) line_events((uint32_t)tid);       // (the coordinator skips need_prefix tiles)
+#endif
             // (B) sequence lines only: walker thread j takes the j-th role-1 line of the tile (every 4th line)
             const uint32_t i_first = (1u - ord0) & 3u;
 #if NTG_STATS
@@ -1281,7 +1400,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 return (uint32_t)s < avail && sb[s] == '>';
             };
             // exclusive max-scan over lines of (end of header line + 1 + HALO): start of the sequence region
-            const uint32_t per = (Cs + 1 + NT - 1) / NT;
+            const uint32_t per = (Cs + 1 + NWK - 1) / NWK;
             const uint32_t i0 = min(tid * per, Cs + 1), i1 = min(i0 + per, Cs + 1);
             uint32_t lm = 0;
             for (uint32_t i = i0; i < i1; i++) if (i < Cs && is_header(i)) lm = max(lm, (uint32_t)S.nl[i] + 1 + HALO);
@@ -1290,14 +1409,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             if (lane == 0) run = 0;
             __shared__ uint32_t s_prev[NT / 32 + 1];
             if (lane == 31) s_prev[tid >> 5] = incl;
-            __syncthreads();
+            tile_sync();
             if (lane == 0 && tid > 0) run = s_prev[(tid >> 5) - 1];
             for (uint32_t i = i0; i < i1; i++) {
                 S.rstart[i] = run;
                 if (i < Cs && is_header(i)) run = max(run, (uint32_t)S.nl[i] + 1 + HALO);
             }
-            __syncthreads();
-            for (uint32_t i = tid; i <= Cs; i += NT) {
+            tile_sync();
+            for (uint32_t i = tid; i <= Cs; i += NWK) {
                 if (is_header(i)) continue;
                 const int a = line_start_rel(i), b = line_end_rel(i);
                 if (b <= a) continue;
@@ -1310,14 +1429,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 #if NTG_STATS
         const long long st_done = clock64();
 #endif
-        __syncthreads();
+        tile_sync();
 #if NTG_STATS
         if (!fasta && !is_coord) { st_walk += st_done - st_mark; st_wait += clock64() - st_done; }
 #endif
         // ---- long lines: SEG-byte pieces shared by the whole CTA
         const uint32_t n_long = min(S.n_long, (uint32_t)LONGMAX);
         // piece length: about one piece per thread when the tile is made of long lines (at least 128 B, at most SEG)
-        const int PSEG = max(128, min(SEG, (int)(((avail + NT - 1) / NT + 15) & ~15u)));
+        const int PSEG = max(128, min(SEG, (int)(((avail + NWK - 1) / NWK + 15) & ~15u)));
         if (n_long) {
             if (tid == 0) {
                 // (order of long_line[] is arbitrary: atomics) -> prefix of piece counts
@@ -1328,9 +1447,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 }
                 S.long_pref[n_long] = sacc;
             }
-            __syncthreads();
+            tile_sync();
             const uint32_t n_pieces = S.long_pref[n_long];
-            for (uint32_t pc = tid; pc < n_pieces; pc += NT) {
+            for (uint32_t pc = tid; pc < n_pieces; pc += NWK) {
                 uint32_t j = 0;
                 while (j + 1 < n_long && S.long_pref[j + 1] <= pc) j++;
                 const uint32_t i = S.long_line[j];
@@ -1340,12 +1459,15 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
                 run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode);
             }
-            __syncthreads();                               // (no long lines: nothing read the tile since the barrier above, and
+            tile_sync();                               // (no long lines: nothing read the tile since the barrier above, and
         }                                                  //  the reset of S.n_long at the next tile stores the value it holds)
         my_seq++;
     }
 
-    if (is_coord && S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);      // the last deferred tile of this CTA
+#if NTG_DC
+    if (tid == 0) { __threadfence_block(); S.dc_total = my_seq; }
+#endif
+    if (!NTG_DC && is_coord && S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);      // the last deferred tile of this CTA
 
 #if NTG_STATS
     {

@@ -12,6 +12,9 @@ declare -A V=(
   [fp64min_ticket]="-DNTG_FP64_MIN=1 -DNTG_TICKET=1"
   [nodefer]="-DNTG_LB_DEFER=0"
   [stats]="-DNTG_STATS=1"
+  [dc]="-DNTG_DC=1"
+  [dc_ticket]="-DNTG_DC=1 -DNTG_TICKET=1"
+  [dc_fp64min]="-DNTG_DC=1 -DNTG_FP64_MIN=1"
 )
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC --expt-relaxed-constexpr -ldl"
 case "${1:-}" in
@@ -20,7 +23,7 @@ case "${1:-}" in
     ls -la needletail_b200/libntgpu_*.so ;;
   run)
     mkdir -p gpurun_out
-    for n in default fp64min ticket fp64min_ticket nodefer stats; do
+    for n in default fp64min ticket fp64min_ticket nodefer stats dc dc_ticket dc_fp64min; do
       so=$PWD/needletail_b200/libntgpu_$n.so; [ -f "$so" ] || continue
       echo "== $n"
       NTGPU_SO=$so timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -1
