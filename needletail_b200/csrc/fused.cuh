@@ -693,6 +693,69 @@ __host__ __device__ __forceinline__ bool walk_clean_fp(const uint8_t* __restrict
 }
 
 
+// The clean walk for 33 <= K <= 63 (experiment NTG_CLEAN2=1, no minimizers: the reference's BitKmer is a u64): F and R are
+// 128-bit, the canonical k-mer is the smaller of the two as a 128-bit number (== the reference's lexicographic byte
+// compare, A<C<G<T), checksums are the wrapping sums of its low and high 64 bits.  Same contract as walk_clean: any byte
+// that is not ACGT/acgt makes it return false with acc untouched.  `comb2` = class bits | complement base pre-shifted for
+// the 32-bit word of R's high half that receives it.
+template <int K>
+struct Clean2Shape {
+    static constexpr int P1 = 2 * (K - 1) - 64;          // bit of R's high 64-bit word where the complement base enters
+    static constexpr int SH = P1 >= 32 ? P1 - 32 : P1;   // ... inside its 32-bit half
+    static constexpr bool ok = K >= 33 && K <= 63 && SH != 0 && SH != 2 && SH != 6;   // must not touch the class bits 0..2 and 7
+};
+template <int K>
+__host__ __device__ __forceinline__ bool walk_clean2(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb2, int ws, int b, Acc& acc) {
+    static_assert(Clean2Shape<K>::ok, "two-word clean walker shape");
+    constexpr int P1 = Clean2Shape<K>::P1, SH = Clean2Shape<K>::SH;
+    constexpr uint32_t RMASK = 3u << SH;
+    constexpr uint64_t M1 = (1ull << (2 * K - 64)) - 1;  // mask of F's high word
+    constexpr int B = 8;
+    uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0, s0 = 0, s1 = 0;
+    uint32_t seen = 0, n_nrc = 0;
+    int p = ws;
+    auto bail = [&]() -> bool {
+#if defined(__CUDA_ARCH__)
+        return __any_sync(__activemask(), (seen & 0x84u) != 0u);
+#else
+        return (seen & 0x84u) != 0u;
+#endif
+    };
+    auto roll = [&](int pp) {
+        const uint32_t u = comb2[sb[pp]];
+        seen |= u;
+        f1 = (f1 << 2) | (f0 >> 62);                 // (unmasked: old bases fall off the top)
+        f0 = (f0 << 2) | (uint64_t)(u & 3u);
+        r0 = (r0 >> 2) | (r1 << 62);
+        r1 = (r1 >> 2) | ((uint64_t)(u & RMASK) << (P1 >= 32 ? 32 : 0));
+    };
+    auto tally = [&]() {
+        const uint64_t fm1 = f1 & M1;
+        const bool lt = lt62(fm1, r1) || (fm1 == r1 && f0 < r0);      // ties => was_rc = true (kmer.rs:124-128)
+        s0 += lt ? f0 : r0;
+        s1 += lt ? fm1 : r1;
+        n_nrc += lt ? 1u : 0u;
+    };
+    {
+        const int e0 = ws + K - 1, e1 = b < e0 ? b : e0;
+#pragma unroll 4
+        for (; p < e1; p++) roll(p);
+    }
+    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
+    while (p + B <= b) {
+#pragma unroll
+        for (int j = 0; j < B; j++) { roll(p + j); tally(); }
+        p += B;
+    }
+    for (; p < b; p++) { roll(p); tally(); }
+    if (seen & 0x84u) return false;
+    const int nk_i = b - (ws + K - 1);
+    const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
+    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
+    acc.ksum_lo += s0; acc.ksum_hi += s1;
+    return true;
+}
+
 // =============================================================================== look-back
 __device__ __forceinline__ SState shfl_state(const SState& v, int src) {
     SState r;
@@ -833,6 +896,9 @@ __device__ __noinline__ void walk_slow(const uint8_t* sb, const uint8_t* lut, in
 #ifndef NTG_LB_WIDE
 #define NTG_LB_WIDE 0                                // 1: warp_lookback_wide (window 32 * NTGPU_LB_G tiles) instead of the 32-tile look-back.
 #endif                                               //    Measured slower (B200, C2: G=1 396, G=2 401-410, G=10 330 vs 425 Gbases/s): kept for A/B only
+#ifndef NTG_CLEAN2
+#define NTG_CLEAN2 0                                 // 1: constant-folded two-word clean walker for k = 51 (walk_clean2)
+#endif
 #ifndef NTG_FP64_MIN
 #define NTG_FP64_MIN 0                               // 1: walk_clean_fp (window minima on the FP64 pipe) for the shapes it covers
 #endif
@@ -858,8 +924,15 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
     const bool had_cr_only = b <= a;
     if (had_cr_only) return;
     const int ws = find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
-    if (FK > 0) {
-        constexpr int CK = FK > 0 ? FK : 21, CM = FK > 0 ? FM : 0;
+    if (FK > 32) {                                           // (NTG_CLEAN2 builds only instantiate this)
+        if (!__any_sync(__activemask(), mode != 0u) && walk_clean2<(FK > 32 ? FK : 51)>(sb, comb, ws, b, acc)) return;
+        mode = 1u;                                             // an item the clean walker refused: the warp's next item goes straight
+        uint32_t any_bad = 0;                                  // to the generic walker, and comes back once an item was all ACGT
+        for (int q = ws; q < b; q++) any_bad |= lut[sb[q]];
+        if (any_bad <= 3u) mode = 0u;
+        walk<KW, MINI, W>(sb, lut, ws, a, b, P, acc, fasta);
+    } else if (FK > 0) {
+        constexpr int CK = (FK > 0 && FK <= 32) ? FK : 21, CM = (FK > 0 && FK <= 32) ? FM : 0;
         bool done = false;
         if (NTG_CLEAN && CK >= 21) {
             if (!__any_sync(__activemask(), mode != 0u)) {
@@ -1053,7 +1126,8 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
     for (int i = tid; i < 256; i += NT) {
         const uint8_t c = class_of(i);
         S.lut[i] = c;
-        const uint32_t ri = (FK >= 17) ? ((3u - (c & 3u)) << (2 * ((FK >= 17 ? FK : 17) - 1) - 32)) : 0u;
+        const uint32_t ri = (FK > 32) ? ((3u - (c & 3u)) << Clean2Shape<(FK > 32 ? FK : 51)>::SH)
+                                      : (FK >= 17) ? ((3u - (c & 3u)) << (2 * ((FK >= 17 && FK <= 32 ? FK : 17) - 1) - 32)) : 0u;
         S.rins[i] = ri;
         S.comb[i] = ri | c;
     }

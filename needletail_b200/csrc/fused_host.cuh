@@ -34,9 +34,15 @@ struct FusedState {
 
 typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
 // kernel variants: three constant-folded headline shapes + the generic ones
+#if NTG_CLEAN2
+#define NTG_FUSED_KERNELS_X2(X) X((k_fused<2, false, 0, 51, 0>))
+#else
+#define NTG_FUSED_KERNELS_X2(X)
+#endif
 #define NTG_FUSED_KERNELS(X) \
     X((k_fused<1, true, 11, 31, 21>)) X((k_fused<1, true, 11, 21, 11>)) X((k_fused<1, false, 0, 31, 0>)) \
-    X((k_fused<2, false, 0, 0, 0>)) X((k_fused<1, false, 0, 0, 0>)) X((k_fused<1, true, 11, 0, 0>)) X((k_fused<1, true, 0, 0, 0>))
+    X((k_fused<2, false, 0, 0, 0>)) X((k_fused<1, false, 0, 0, 0>)) X((k_fused<1, true, 11, 0, 0>)) X((k_fused<1, true, 0, 0, 0>)) \
+    NTG_FUSED_KERNELS_X2(X)
 static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) {
     using namespace fused;
     if (has_query) {                           // the query count lives in the generic walkers only
@@ -44,6 +50,9 @@ static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) 
         if (m == 0) return k_fused<1, false, 0, 0, 0>;
         return (k - m + 1 == 11) ? k_fused<1, true, 11, 0, 0> : k_fused<1, true, 0, 0, 0>;
     }
+#if NTG_CLEAN2
+    if (k == 51 && m == 0) return k_fused<2, false, 0, 51, 0>;
+#endif
     if (k == 31 && m == 21) return k_fused<1, true, 11, 31, 21>;
     if (k == 21 && m == 11) return k_fused<1, true, 11, 21, 11>;
     if (k == 31 && m == 0) return k_fused<1, false, 0, 31, 0>;

@@ -35,7 +35,7 @@ template <int K> static Luts make_luts() {
     return l;
 }
 static bool same(const Acc& a, const ntref::Tallies& t, bool mini) {
-    return a.n_kmers == t.n_kmers && a.n_not_rc == t.n_not_rc && a.ksum_lo == t.kmer_sum_lo &&
+    return a.n_kmers == t.n_kmers && a.n_not_rc == t.n_not_rc && a.ksum_lo == t.kmer_sum_lo && a.ksum_hi == t.kmer_sum_hi &&
            (!mini || (a.n_mini == t.n_minimizers && a.msum == t.minimizer_sum));
 }
 
@@ -211,6 +211,55 @@ static int test_first_lines_event(std::mt19937_64& rng) {
     return fails;
 }
 
+// walk_clean2 (33 <= K <= 63, two-word k-mers) and the generic two-word walker against the oracle
+template <int K>
+static int run2(std::mt19937_64& rng, int iters, const char* name) {
+    uint32_t comb2[256];
+    for (int b = 0; b < 256; b++) comb2[b] = ((3u - (g_cls[b] & 3u)) << fused::Clean2Shape<K>::SH) | g_cls[b];
+    int fails = 0; long n_clean = 0;
+    std::vector<uint8_t> norm, rc;
+    for (int it = 0; it < iters && fails < 5; it++) {
+        const int flavour = (int)(rng() % 3);                 // 0: clean, 1: a few non-ACGT, 2: + whitespace
+        const int n = (int)(rng() % (it % 5 == 0 ? 900 : 300));
+        std::string s(n, 'A');
+        for (auto& c : s) {
+            const uint64_t r = rng();
+            c = "ACGTacgt"[r & 7];
+            const unsigned roll = (unsigned)((r >> 8) % 1000);
+            if (flavour >= 1 && roll < 6u) c = "NnRY-.Xx"[(r >> 20) % 8];
+            if (flavour >= 2 && roll >= 992) c = " \t\r"[(r >> 30) % 3];
+        }
+        if (it % 9 == 0) for (auto& c : s) c = (rng() % 40) ? 'A' : 'T';      // low complexity: long runs, F == R prefixes
+        const uint8_t* sb = (const uint8_t*)s.data();
+        ntref::Tallies t;
+        ntref::tally_sequence(sb, (size_t)n, K, 0, false, nullptr, t, norm, rc);
+        auto frag = [&](int a, int b, bool clean_first, Acc& acc) {
+            if (b > a && sb[b - 1] == '\r') b--;
+            if (b <= a) return;
+            uint32_t slow = 0;
+            const int ws = fused::find_ws(sb, g_cls, a, 0, true, K, slow);
+            if (clean_first && fused::walk_clean2<K>(sb, comb2, ws, b, acc)) { n_clean++; return; }
+            Params P{}; P.k = K; P.m = 0; P.w = 1; P.has_query = 0;
+            fused::walk<2, false, 0>(sb, g_cls, ws, a, b, P, acc, false);
+        };
+        int c1 = n ? (int)(rng() % (unsigned)n) : 0, c2 = n ? (int)(rng() % (unsigned)n) : 0;
+        if (c1 > c2) std::swap(c1, c2);
+        for (int mode = 0; mode < 4; mode++) {                // whole / fragments  x  clean-first / generic only
+            Acc acc;
+            if (mode < 2) frag(0, n, mode == 0, acc);
+            else { frag(0, c1, mode == 2, acc); frag(c1, c2, mode == 2, acc); frag(c2, n, mode == 2, acc); }
+            if (!same(acc, t, false)) {
+                std::printf("%s: mismatch (mode %d) n=%d cuts %d,%d: kmers %llu/%llu not_rc %llu/%llu lo %llx/%llx hi %llx/%llx\n", name, mode, n, c1, c2,
+                            (unsigned long long)acc.n_kmers, (unsigned long long)t.n_kmers, (unsigned long long)acc.n_not_rc, (unsigned long long)t.n_not_rc,
+                            (unsigned long long)acc.ksum_lo, (unsigned long long)t.kmer_sum_lo, (unsigned long long)acc.ksum_hi, (unsigned long long)t.kmer_sum_hi);
+                fails++;
+            }
+        }
+    }
+    std::printf("%s: %d items, clean two-word walks %ld; %s\n", name, iters, n_clean, fails ? "FAIL" : "ok");
+    return fails;
+}
+
 int main() {
     build_cls();
     std::mt19937_64 rng(20240917);
@@ -221,6 +270,9 @@ int main() {
     fails += run<31, 0>(rng, 6000, "k31 m0");
     fails += run<31, 31>(rng, 1500, "k31 m31");
     fails += run<25, 24>(rng, 1500, "k25 m24");
+    fails += run2<51>(rng, 4000, "k51");
+    fails += run2<63>(rng, 1500, "k63");
+    fails += run2<35>(rng, 1500, "k35");
     if (fails) { std::printf("walkers FAILED\n"); return 1; }
     std::printf("walkers ok\n");
     return 0;

@@ -2,6 +2,7 @@
 # A/B of compile-time experiment builds of libntgpu on one GPU box (same box, back to back):
 #   tools/ab_variants.sh build            # here (no GPU): builds needletail_b200/libntgpu_<name>.so for every variant
 #   gpurun --timeout 900 -- 'bash tools/ab_variants.sh run'    # on the box: GPU parity tests + per-config throughput per variant
+# (clean2 only matters for k = 51: run it with NT_MC_ONLY=4.)
 # Variants are sets of -D flags of needletail_b200/csrc/fused.cuh; "default" is the shipped build.
 set -u
 cd "$(dirname "$0")/.."
@@ -12,6 +13,7 @@ declare -A V=(
   [fp64min_ticket]="-DNTG_FP64_MIN=1 -DNTG_TICKET=1"
   [nodefer]="-DNTG_LB_DEFER=0"
   [stats]="-DNTG_STATS=1"
+  [clean2]="-DNTG_CLEAN2=1"
   [dc]="-DNTG_DC=1"
   [dc_ticket]="-DNTG_DC=1 -DNTG_TICKET=1"
   [dc_fp64min]="-DNTG_DC=1 -DNTG_FP64_MIN=1"
@@ -23,7 +25,7 @@ case "${1:-}" in
     ls -la needletail_b200/libntgpu_*.so ;;
   run)
     mkdir -p gpurun_out
-    for n in default fp64min ticket fp64min_ticket nodefer stats dc dc_ticket dc_fp64min; do
+    for n in default fp64min ticket fp64min_ticket nodefer stats clean2 dc dc_ticket dc_fp64min; do
       so=$PWD/needletail_b200/libntgpu_$n.so; [ -f "$so" ] || continue
       echo "== $n"
       NTGPU_SO=$so timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -1
