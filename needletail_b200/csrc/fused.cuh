@@ -1135,6 +1135,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0;
 #if NTG_DC
         S.dc_head = 0; S.dc_tail = 0; S.dc_total = 0xffffffffu;
+        for (int i = 0; i < DC_R; i++) S.dc[i].prefix_ready = 0;      // (shared memory is not zeroed: seq + 1 must never match by accident)
 #endif
     }
     __syncthreads();
