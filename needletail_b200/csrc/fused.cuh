@@ -275,6 +275,25 @@ __host__ __device__ __forceinline__ int find_ws(const uint8_t* __restrict__ sb, 
     return ws;
 }
 
+// find_ws that also returns the warm-up bases themselves, packed 2 bits each with the base next to `a` in bits 0..1, and their
+// number.  For walk_clean_w: a warm-up that crosses deleted bytes (wrapped FASTA: the newline before every line) is
+// handed over as codes, so that the item proper stays free of deleted bytes.
+__host__ __device__ __forceinline__ int find_ws_codes(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int a, int lo, bool lo_exact,
+                                             int k, uint32_t& slow, int& got_out, uint64_t& codes_out) {
+    int ws = a, got = 0, p = a - 1;
+    uint64_t codes = 0;
+    bool stopped = false;
+    while (p >= lo && got < k - 1) {
+        const uint8_t c = lut[sb[p]];
+        if (c <= 3) { codes |= (uint64_t)c << (2 * got); got++; ws = p; }
+        else if (c == 4) { stopped = true; break; }         // a non-ACGT base resets everything before it
+        p--;
+    }
+    if (!stopped && got < k - 1 && p < lo && !lo_exact) slow |= FLAG_HALO_OVERFLOW;
+    got_out = got; codes_out = codes;
+    return ws;
+}
+
 template <int KW, bool MINI, int W>
 __host__ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, const uint8_t* __restrict__ lut, int ws, int a, int b,
                                      const Params& P, Acc& acc, bool count_bases) {
@@ -580,6 +599,121 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     if (MINI) { acc.n_mini += nk; acc.msum += s_m; }
     return true;
 }
+
+// walk_clean for an item whose warm-up is given as K-1 packed codes (find_ws_codes) instead of bytes (experiment NTG_WRAP=1):
+// lines of wrapped FASTA, whose warm-up crosses the previous line break.  Requires exactly K-1 warm-up bases.
+template <int K, int M>
+__host__ __device__ __forceinline__ bool walk_clean_w(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int a, int b, uint64_t wcodes, Acc& acc) {
+    static_assert(K >= 21 && K <= 31 && M >= 0 && M <= K, "clean walker shape (class bits 0..7 must not overlap the R insert)");
+    constexpr bool MINI = M > 0;
+    constexpr int W = MINI ? K - M + 1 : 1;
+    constexpr int B = MINI ? W : 8;                  // bases per unrolled block
+    constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
+    constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
+    constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
+    constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
+    constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
+    uint64_t f = 0, r = 0, s_k = 0, s_m = 0, pre = 0;
+    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
+    uint64_t buf[W + 1];
+#pragma unroll
+    for (int i = 0; i <= W; i++) buf[i] = 0;
+    int p = a;
+
+    // Leave as soon as a lane of the (converged part of the) warp has met a byte this walker cannot handle: the warp then
+    // redoes its items with walk_fast together instead of finishing a walk whose result is thrown away.  A hint only:
+    // exactness rests on each lane's own `seen` test at the end.
+    auto bail = [&]() -> bool {
+#if defined(__CUDA_ARCH__)
+        return __any_sync(__activemask(), (seen & 0x84u) != 0u);
+#else
+        return (seen & 0x84u) != 0u;
+#endif
+    };
+    auto roll = [&](int pp) {
+        const uint32_t u = comb[sb[pp]];
+        seen |= u;
+        f = (f << 2) | (uint64_t)(u & 3u);
+        r = (r >> 2) | ((uint64_t)(u & RMASK) << 32);
+    };
+    // score of the m-mer x ending here: min(x, RC_k(x)), RC_k(x) = R | LMASK (bitkmer.rs:146-162).  RC_k(x) can only be
+    // the smaller one when R < 4^M, i.e. when the last K-M bases are all T (4^-(K-M) per position in random sequence):
+    // RARE shapes take x and only remember the smallest top part of R seen; an item where that ever reached zero
+    // is handed to walk_fast like one with a non-ACGT base.
+    auto score = [&]() -> uint64_t {
+        const uint64_t x = f & MMASK;
+        if (RARE) {
+            const uint32_t top = (2 * M >= 32) ? (uint32_t)(r >> 32) : (uint32_t)(r >> (2 * M));
+            rtop_min = top < rtop_min ? top : rtop_min;
+            return x;
+        }
+        const uint64_t y = r | LMASK;
+        return lt62(x, y) ? x : y;
+    };
+    auto tally = [&](uint64_t win) {
+        const uint64_t fm = f & KMASK;
+        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
+        s_k += lt ? fm : r;
+        n_nrc += lt ? 1u : 0u;
+        if (MINI) s_m += win;
+    };
+    // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
+    auto block = [&](auto check) {
+        constexpr bool CHECK = decltype(check)::value;
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            if (CHECK && p + j >= b) return;
+            roll(p + j);
+            uint64_t win = 0;
+            if (MINI) {
+                const uint64_t sc = score();
+                if (j == 0) {
+                    pre = (W == 1 || lt62(sc, pre)) ? sc : pre;
+                    win = pre;
+                    buf[W - 1] = sc;
+#pragma unroll
+                    for (int q = W - 2; q >= 1; q--) buf[q] = lt62(buf[q], buf[q + 1]) ? buf[q] : buf[q + 1];
+                } else {
+                    const int i = j - 1;
+                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                    win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
+                    buf[i] = sc;
+                }
+            }
+            tally(win);
+        }
+    };
+
+    // head: the K-1 warm-up bases come from the register (code h = bits 2(K-2-h).., h = 0 the farthest); M-1 of them only feed
+    // F / R, the other W-1 are the first scores.  Every base of the item proper [a,b) then ends a k-mer.
+    {
+        auto roll_code = [&](uint32_t code) {
+            f = (f << 2) | (uint64_t)code;
+            r = (r >> 2) | ((uint64_t)((3u - code) << (2 * (K - 1) - 32)) << 32);
+        };
+#pragma unroll
+        for (int h = 0; h < K - 1; h++) {
+            roll_code((uint32_t)(wcodes >> (2 * (K - 2 - h))) & 3u);
+            if (MINI && h >= M - 1) {
+                const int i = h - (M - 1);
+                const uint64_t sc = score();
+                pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                buf[i] = sc;
+            }
+        }
+    }
+    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
+    while (p + B <= b) { block(FalseT{}); p += B; if (NTG_BAIL_VOTE >= 2 && bail()) return false; }
+    if (p < b) block(TrueT{});
+    if ((seen & 0x84u) || (RARE && rtop_min < RTOP_LIMIT)) return false;
+    const int nk_i = b - a;
+    const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
+    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
+    acc.ksum_lo += s_k;
+    if (MINI) { acc.n_mini += nk; acc.msum += s_m; }
+    return true;
+}
+
 
 // The same walk with the window minima on the FP64 pipe (experiment, NTG_FP64_MIN=1; measured in round 2): the three
 // 64-bit minima per base cost the INT pipe 2 SEL each on top of the DSETP; m-mer scores are below 2^42, so they can
@@ -896,6 +1030,9 @@ __device__ __noinline__ void walk_slow(const uint8_t* sb, const uint8_t* lut, in
 #ifndef NTG_LB_WIDE
 #define NTG_LB_WIDE 0                                // 1: warp_lookback_wide (window 32 * NTGPU_LB_G tiles) instead of the 32-tile look-back.
 #endif                                               //    Measured slower (B200, C2: G=1 396, G=2 401-410, G=10 330 vs 425 Gbases/s): kept for A/B only
+#ifndef NTG_WRAP
+#define NTG_WRAP 0                                   // 1: walk_clean_w for items whose warm-up crosses deleted bytes (wrapped FASTA)
+#endif
 #ifndef NTG_CLEAN2
 #define NTG_CLEAN2 0                                 // 1: constant-folded two-word clean walker for k = 51 (walk_clean2)
 #endif
@@ -923,7 +1060,19 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
     if (b > a && sb[b - 1] == '\r') b--;                   // a trailing '\r' is deleted by normalize: nothing to walk
     const bool had_cr_only = b <= a;
     if (had_cr_only) return;
+#if NTG_WRAP
+    int got = 0; uint64_t wcodes = 0;
+    const int ws = find_ws_codes(sb, lut, a, lo, lo_exact, (int)P.k, slow, got, wcodes);
+    if (FK >= 21 && FK <= 31 && got == FK - 1 && a - ws != got && !__any_sync(__activemask(), mode != 0u)) {
+        // the warm-up crosses deleted bytes (wrapped FASTA: the previous line break): feed it from the register
+        if (walk_clean_w<(FK >= 21 && FK <= 31 ? FK : 21), (FK >= 21 && FK <= 31 ? FM : 0)>(sb, comb, a, b, wcodes, acc)) {
+            if (fasta) acc.n_bases += (uint64_t)(b - a);
+            return;
+        }
+    }
+#else
     const int ws = find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
+#endif
     if (FK > 32) {                                           // (NTG_CLEAN2 builds only instantiate this)
         if (!__any_sync(__activemask(), mode != 0u) && walk_clean2<(FK > 32 ? FK : 51)>(sb, comb, ws, b, acc)) return;
         mode = 1u;                                             // an item the clean walker refused: the warp's next item goes straight

@@ -260,6 +260,50 @@ static int run2(std::mt19937_64& rng, int iters, const char* name) {
     return fails;
 }
 
+// wrapped sequences: items are the lines; a line's warm-up crosses the previous line break and is fed to walk_clean_w as codes
+template <int K, int M>
+static int run_wrapped(std::mt19937_64& rng, int iters, const char* name) {
+    const Luts L = make_luts<K>();
+    int fails = 0; long n_w = 0, n_other = 0;
+    std::vector<uint8_t> norm, rc;
+    for (int it = 0; it < iters && fails < 5; it++) {
+        const int n = 1 + (int)(rng() % 600), width = 20 + (int)(rng() % 70);
+        const bool crlf = rng() % 3 == 0, dirty = rng() % 4 == 0;
+        std::string s;
+        std::vector<std::pair<int, int>> lines;             // [a, b) of every line, line break excluded
+        for (int i = 0, col = 0, a = 0; i < n; i++) {
+            char c = "ACGTacgt"[rng() & 7];
+            if (dirty && rng() % 97 == 0) c = 'N';
+            s += c;
+            if (++col == width || i == n - 1) {
+                lines.push_back({a, (int)s.size()});
+                if (i != n - 1 || rng() % 2) s += crlf ? "\r\n" : "\n";
+                a = (int)s.size(); col = 0;
+            }
+        }
+        const uint8_t* sb = (const uint8_t*)s.data();
+        ntref::Tallies t;
+        ntref::tally_sequence(sb, s.size(), K, M, false, nullptr, t, norm, rc);
+        Acc acc;
+        for (auto [a, b] : lines) {
+            if (b <= a) continue;
+            uint32_t slow = 0; int got = 0; uint64_t wcodes = 0;
+            const int ws = fused::find_ws_codes(sb, g_cls, a, 0, true, K, slow, got, wcodes);
+            if (got == K - 1 && a - ws != got && fused::walk_clean_w<K, M>(sb, L.comb, a, b, wcodes, acc)) { n_w++; continue; }
+            n_other++;
+            item<K, M>(sb, L, a, b, 0, CLEAN | FAST | GENERIC, acc);
+        }
+        if (!same(acc, t, M > 0)) {
+            std::printf("%s: wrapped mismatch n=%d width=%d: kmers %llu/%llu mini %llu/%llu msum %llx/%llx\n", name, n, width, (unsigned long long)acc.n_kmers,
+                        (unsigned long long)t.n_kmers, (unsigned long long)acc.n_mini, (unsigned long long)t.n_minimizers, (unsigned long long)acc.msum,
+                        (unsigned long long)t.minimizer_sum);
+            fails++;
+        }
+    }
+    std::printf("%s wrapped: %d sequences, %ld lines through walk_clean_w, %ld through the other walkers; %s\n", name, iters, n_w, n_other, fails ? "FAIL" : "ok");
+    return fails;
+}
+
 int main() {
     build_cls();
     std::mt19937_64 rng(20240917);
@@ -270,6 +314,9 @@ int main() {
     fails += run<31, 0>(rng, 6000, "k31 m0");
     fails += run<31, 31>(rng, 1500, "k31 m31");
     fails += run<25, 24>(rng, 1500, "k25 m24");
+    fails += run_wrapped<31, 21>(rng, 3000, "k31 m21");
+    fails += run_wrapped<21, 11>(rng, 3000, "k21 m11");
+    fails += run_wrapped<31, 0>(rng, 2000, "k31 m0");
     fails += run2<51>(rng, 4000, "k51");
     fails += run2<63>(rng, 1500, "k63");
     fails += run2<35>(rng, 1500, "k35");

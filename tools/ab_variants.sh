@@ -14,6 +14,7 @@ declare -A V=(
   [nodefer]="-DNTG_LB_DEFER=0"
   [stats]="-DNTG_STATS=1"
   [clean2]="-DNTG_CLEAN2=1"
+  [wrap]="-DNTG_WRAP=1"
   [dc]="-DNTG_DC=1"
   [dc_ticket]="-DNTG_DC=1 -DNTG_TICKET=1"
   [dc_fp64min]="-DNTG_DC=1 -DNTG_FP64_MIN=1"
@@ -25,7 +26,7 @@ case "${1:-}" in
     ls -la needletail_b200/libntgpu_*.so ;;
   run)
     mkdir -p gpurun_out
-    for n in default fp64min ticket fp64min_ticket nodefer stats clean2 dc dc_ticket dc_fp64min; do
+    for n in default fp64min ticket fp64min_ticket nodefer stats clean2 wrap dc dc_ticket dc_fp64min; do
       so=$PWD/needletail_b200/libntgpu_$n.so; [ -f "$so" ] || continue
       echo "== $n"
       NTGPU_SO=$so timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -1
