@@ -17,7 +17,30 @@ CONFIGS = [
     ("C4 100M x 150bp FASTQ 1% N k=31 m=21 (one GPU's shard)", "fastq", 100_000_000, 150, 31, 21, 655, 0x5EED0004),
     ("C3 shape, 4M x 10kbp FASTA k=21 m=11 (40 of the 100 Gbases)", "fasta", 4_000_000, 10_000, 21, 11, 0, 0x5EED0003),
     ("C5 shape, 50M x 250bp FASTQ k=51 (text resident; gzip inflate is host work)", "fastq", 50_000_000, 250, 51, 0, 0, 0x5EED0005),
+    # not a BASELINE config: the same FASTA shape wrapped at 70 columns (what genome FASTA files look like); generated on the host
+    ("C3w 120k x 10kbp FASTA wrapped at 70 columns, k=21 m=11 (host-generated, 1.2 GB)", "fasta_wrapped", 120_000, 10_000, 21, 11, 0, 0x5EED0013),
 ]
+
+
+def wrapped_fasta(reads, L, width, seed):
+    """reads records '>r%08d\\n' + L random ACGT bases wrapped at `width` columns, as one uint8 array (numpy, host)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    full, rest = divmod(L, width)
+    body = full * (width + 1) + (rest + 1 if rest else 0)
+    ids = np.char.add(">r", np.char.zfill(np.arange(reads).astype(str), 8))
+    hdr = np.frombuffer("".join(i + "\n" for i in ids).encode(), dtype=np.uint8).reshape(reads, 11)
+    out = np.empty((reads, 11 + body), dtype=np.uint8)
+    out[:, :11] = hdr
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(reads, L), dtype=np.uint8)]
+    if full:
+        blk = out[:, 11:11 + full * (width + 1)].reshape(reads, full, width + 1)
+        blk[:, :, :width] = bases[:, :full * width].reshape(reads, full, width)
+        blk[:, :, width] = 10
+    if rest:
+        out[:, 11 + full * (width + 1):11 + full * (width + 1) + rest] = bases[:, full * width:]
+        out[:, -1] = 10
+    return out.reshape(-1)
 
 
 def main():
@@ -26,10 +49,17 @@ def main():
     only = os.environ.get("NT_MC_ONLY")
     configs = [CONFIGS[int(i)] for i in only.split(",")] if only else CONFIGS
     for name, kind, reads, L, k, m, nth, seed in configs:
-        rb = 2 * L + 16 if kind == "fastq" else L + 12
-        nbytes = reads * rb
-        d = ctx.device_alloc(nbytes)
-        (ctx.synth_fastq_device if kind == "fastq" else ctx.synth_fasta_device)(d, seed, 0, reads, L, nth)
+        if kind == "fasta_wrapped":
+            host = wrapped_fasta(reads, L, 70, seed)
+            nbytes = int(host.size)
+            d = ctx.device_alloc(nbytes)
+            ctx.h2d(d, host)
+            del host
+        else:
+            rb = 2 * L + 16 if kind == "fastq" else L + 12
+            nbytes = reads * rb
+            d = ctx.device_alloc(nbytes)
+            (ctx.synth_fastq_device if kind == "fastq" else ctx.synth_fasta_device)(d, seed, 0, reads, L, nth)
         ctx.sync()
         ms = []
         t = None
