@@ -200,3 +200,14 @@ def test_record_from_table_row():
     r = nt.Record._from_table(data, row, "fasta")
     assert (r.id, r.seq, r.qual, r.raw_seq, r.num_bases) == ("x", "ACGT", None, b"AC\nGT", 4) and r.is_fasta()
     assert str(r) == ">x\nACGT\n" and r == nt.Record("x", "ACGT")
+
+
+def test_experiment_builds_compile(tmp_path):
+    """The compile-time A/B experiments of fused.cuh (tools/ab_variants.sh) stay buildable: one nvcc pass with all of them on."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    flags = ["-DNTG_FP64_MIN=1", "-DNTG_TICKET=1", "-DNTG_DC=1", "-DNTG_STATS=1", "-DNTG_CLEAN2=1", "-DNTG_WRAP=1", "-DNTG_LB_WIDE=1"]
+    out = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr", *flags, "-cubin",
+                          "-o", str(tmp_path / "all_on.cubin"), os.path.join(ROOT, "needletail_b200", "csrc", "ntgpu.cu")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
