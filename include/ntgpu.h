@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NTG_ABI_VERSION 1
+#define NTG_ABI_VERSION 2
 
 typedef enum ntg_status {
     NTG_OK = 0,
@@ -184,7 +184,10 @@ typedef struct ntg_tally_config {
     uint32_t allow_iupac;      /* normalize(iupac) flag (does not change the tallies)    */
     uint32_t has_query;        /* count canonical k-mers equal to `query` (lib.rs:31-35) */
     uint8_t query[64];         /* k ASCII bases ACGT                                     */
+    uint32_t flags;            /* NTG_TALLY_* bits, 0 for normal use                     */
 } ntg_tally_config;
+/* diagnostic: FASTQ tiles wait for the look-back instead of starting on the locally inferred line phase (same results) */
+#define NTG_TALLY_NO_SPECULATION 1u
 
 typedef struct ntg_tallies {
     uint64_t n_records;
@@ -198,7 +201,7 @@ typedef struct ntg_tallies {
     uint64_t minimizer_sum;    /* wrapping sum of bitkmer::minimizer(kmer, m).0          */
     uint64_t reserved[7];      /* reserved[0]: 0 = single-pass fused kernel produced these; else bitmask of why the exact
                                   record-table path re-ran (1 parse error, 2 newline-dense tile, 4 whitespace run > halo);
-                                  reserved[1]: non-zero when the warp-specialised short-read kernel handed over to the general kernel */
+                                  reserved[1]: non-zero when a speculated FASTQ line phase was wrong and the call re-ran without speculation */
 } ntg_tallies;
 
 /* host bytes: H2D copies are pipelined with the kernel inside the call (the end-to-end path) */

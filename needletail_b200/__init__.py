@@ -69,7 +69,7 @@ class _Items(C.Structure):
 
 class _TallyConfig(C.Structure):
     _fields_ = [("k", C.c_uint32), ("m", C.c_uint32), ("allow_iupac", C.c_uint32), ("has_query", C.c_uint32),
-                ("query", C.c_uint8 * 64)]
+                ("query", C.c_uint8 * 64), ("flags", C.c_uint32)]
 
 
 class _Tallies(C.Structure):
@@ -320,9 +320,10 @@ class Context:
         return out
 
     # ---- (3) fused hot path
-    @staticmethod
-    def _cfg(k, m, iupac, query):
-        cfg = _TallyConfig(k=k, m=m, allow_iupac=int(iupac), has_query=int(query is not None))
+    tally_flags = 0          # NTG_TALLY_* bits sent with every tally call (1 = no FASTQ line-phase speculation; diagnostic)
+
+    def _cfg(self, k, m, iupac, query):
+        cfg = _TallyConfig(k=k, m=m, allow_iupac=int(iupac), has_query=int(query is not None), flags=self.tally_flags)
         if query is not None:
             q = bytes(query)
             for i, b in enumerate(q[:64]):

@@ -35,15 +35,8 @@ constexpr int MAXROUNDS = (TILE / ROWB + NTW - 1) / NTW;   // 2  (rows are scann
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
 constexpr int NLMAX = 2048;              // newline capacity per tile (mean line >= 42 B at full tile size)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
-constexpr int CHUNK = 1;                 // tiles claimed per ticket. (>1 chains prefixes inside a CTA but serialises chunks:
-                                         // a chunk's first tile then waits for the LAST tile of the previous chunk - measured 3700x slower)
 constexpr int LONGMAX = TILE / SEG + 2;
-#ifndef NTG_DC
-#define NTG_DC 0                         // 1: decoupled coordinator (experiment): the coordinator warp leaves the CTA barriers and trails the
-#endif                                   //    walkers through a small ring of per-tile records; walker thread 0 publishes the aggregates
-constexpr int NWK = NTG_DC ? NTW : NT;   // threads that run the tile loop's cooperative phases
-constexpr int DC_R = 8;                  // ring depth of the decoupled coordinator
-constexpr int LB_GMAX = 12;              // look-back: at most this many tiles per lane and step (one step spans <= 384 tiles)
+constexpr int NWK = NT;                  // threads that run the tile loop's cooperative phases
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
 
@@ -100,7 +93,6 @@ struct Params {
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
     int has_query;
     uint32_t one;                      // == 1 (run-time constant for mad.wide)
-    uint32_t lb_g;                     // look-back: tiles per lane and step (window = 32 * lb_g tiles), 1..LB_GMAX
     uint32_t spec;                     // FASTQ: walkers start on a locally inferred line phase while the coordinator warp
                                        // does the look-back; a wrong guess raises FLAG_SPEC_MISS and the host re-runs with spec = 0
     uint64_t q_lo, q_hi;
@@ -161,7 +153,6 @@ struct __align__(16) Smem {
     uint32_t warp_tmp[NT / 32 + 2];
     uint64_t red[NT / 32][9];
     SState prefix;                     // exclusive prefix of this tile
-    SState last_inc;                   // inclusive prefix of the previous tile of this CTA's chunk
     volatile uint32_t prefix_seq;      // number of tiles of this CTA whose prefix has been resolved by the coordinator
     // the tile whose look-back the coordinator has deferred by one tile (speculative FASTQ, see P2c); coordinator warp only
     SState pend_agg;
@@ -169,18 +160,8 @@ struct __align__(16) Smem {
     uint32_t pend_guess, pend_cs, pend_avail, pend_line0;
     uint32_t pend_nl4[4];              // the tile's first four newline offsets
     volatile uint32_t pend_valid;
-#if NTG_DC
-    struct DcRec {                     // what the decoupled coordinator needs of a tile once the tile has left shared memory
-        SState agg, prefix;
-        uint64_t t;
-        uint32_t guess, cs, avail, line0, need_prefix;
-        uint32_t nl4[4];
-        volatile uint32_t prefix_ready;    // seq + 1 once `prefix` is valid (tiles whose walkers wait for it)
-    } dc[DC_R];
-    volatile uint32_t dc_head, dc_tail, dc_total;   // records produced / consumed; number of tiles of this CTA (0xffffffff until known)
-#endif
-    uint32_t tile_idx;
-    uint32_t tile_idx_next;            // ticket of the next tile, claimed by the coordinator during this one
+    uint32_t one_word;                 // == 1: read back into a (non-uniform) register, the multiplier of the FMA-pipe moves
+    uint32_t tile_idx_next;            // ticket of this CTA's next tile, claimed by walker thread 0 at the end of its walk
     uint32_t n_long;
     uint32_t long_line[LONGMAX];       // line indices of long sequence lines
     uint32_t long_pref[LONGMAX + 1];   // exclusive prefix of piece counts
@@ -188,13 +169,7 @@ struct __align__(16) Smem {
 };
 
 // barrier of the threads that run the tile loop (all of the CTA, or the walkers only when the coordinator is decoupled)
-__device__ __forceinline__ void tile_sync() {
-#if NTG_DC
-    asm volatile("bar.sync 1, %0;" ::"n"(NTW) : "memory");
-#else
-    __syncthreads();
-#endif
-}
+__device__ __forceinline__ void tile_sync() { __syncthreads(); }
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* tmp) {
     constexpr int NW = NWK / 32;
     uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
@@ -371,9 +346,6 @@ __host__ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, co
 //  - checksums are carried per item as a 64-bit sum of the low words and a 32-bit sum of the high words
 //    (3 integer adds per value) and folded when the item ends;
 //  - non-ACGT bases never branch: they only push `next_ok`, the first index where a k-mer may end.
-#ifndef NTG_BAIL_VOTE
-#define NTG_BAIL_VOTE 1                              // walk_clean leaves early on a warp vote: 0 never, 1 after the head, 2 after every block
-#endif
 struct FalseT { static constexpr bool value = false; };
 struct TrueT { static constexpr bool value = true; };
 struct FastLuts {
@@ -478,6 +450,56 @@ __host__ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ s
 }
 
 
+// ---- pipe-balancing helpers (round 2).  Measured on B200 (tools/ubench/pipes.cu, profiles/r2a_*): SEL, FSEL, LOP3, SHF, IADD3,
+// PRMT, VIMNMX and ISETP all issue on the ALU pipe (2 cycles per warp instruction), IMAD / IMAD.WIDE / IMAD.MOV on the FMA pipe
+// (2 cycles), DSETP on the FP64 pipe (~4.5 cycles); instructions of different pipes overlap (pairs cost ~2.05 cycles).  The
+// clean walker's main loop was 19 ALU : 7 FMA instructions per base, i.e. ALU-pipe bound.  A 64-bit select is two SELs (ALU);
+// the same effect is had on the FMA pipe with two PREDICATED multiply-adds by a run-time 1 (`one`, which ptxas cannot fold
+// into a SEL): a conditional move "@p d = s * one + 0", or a conditional accumulate "@p acc += s * one".
+#ifndef NTG_WV
+#define NTG_WV 0                                     // bit 0 pairwise 3-input checksum adds, bit 1 canonical pick accumulated on the FMA pipe,
+#endif                                               // bit 2 prefix minimum, bit 3 suffix pass, bit 4 window pick on the FMA pipe
+// dst = min(dst, src), both below 2^62
+template <bool FMA>
+__host__ __device__ __forceinline__ void min62_into(uint64_t& dst, uint64_t src, uint32_t one) {
+#ifdef __CUDA_ARCH__
+    if (FMA) {
+        asm("{\n\t.reg .pred p;\n\t.reg .f64 a, b;\n\t.reg .u32 dl, dh, sl, sh;\n\t"
+            "mov.b64 a, %0;\n\tmov.b64 b, %1;\n\tmov.b64 {dl, dh}, %0;\n\tmov.b64 {sl, sh}, %1;\n\t"
+            "setp.lt.f64 p, b, a;\n\t@p mad.lo.u32 dl, sl, %2, 0;\n\t@p mad.lo.u32 dh, sh, %2, 0;\n\t"
+            "mov.b64 %0, {dl, dh};\n\t}" : "+l"(dst) : "l"(src), "r"(one));
+        return;
+    }
+#endif
+    (void)one;
+    dst = lt62(src, dst) ? src : dst;
+}
+// lo64 += low word of min(a, b); hi32 += its high word; cnt += (a < b)   (a, b below 2^62; COUNT = false leaves cnt alone)
+template <bool COUNT>
+__host__ __device__ __forceinline__ void min62_accumulate_fma(uint64_t& lo64, uint32_t& hi32, uint32_t& cnt, uint64_t a, uint64_t b, uint32_t one) {
+#ifdef __CUDA_ARCH__
+    if (COUNT)
+        asm("{\n\t.reg .pred p;\n\t.reg .f64 x, y;\n\t.reg .u32 al, ah, bl, bh;\n\t"
+            "mov.b64 x, %3;\n\tmov.b64 y, %4;\n\tmov.b64 {al, ah}, %3;\n\tmov.b64 {bl, bh}, %4;\n\t"
+            "setp.lt.f64 p, x, y;\n\t@p mad.wide.u32 %0, al, %5, %0;\n\t@!p mad.wide.u32 %0, bl, %5, %0;\n\t"
+            "@p mad.lo.u32 %1, ah, %5, %1;\n\t@!p mad.lo.u32 %1, bh, %5, %1;\n\t@p mad.lo.u32 %2, %5, %5, %2;\n\t}"
+            : "+l"(lo64), "+r"(hi32), "+r"(cnt) : "l"(a), "l"(b), "r"(one));
+    else
+        asm("{\n\t.reg .pred p;\n\t.reg .f64 x, y;\n\t.reg .u32 al, ah, bl, bh;\n\t"
+            "mov.b64 x, %2;\n\tmov.b64 y, %3;\n\tmov.b64 {al, ah}, %2;\n\tmov.b64 {bl, bh}, %3;\n\t"
+            "setp.lt.f64 p, x, y;\n\t@p mad.wide.u32 %0, al, %4, %0;\n\t@!p mad.wide.u32 %0, bl, %4, %0;\n\t"
+            "@p mad.lo.u32 %1, ah, %4, %1;\n\t@!p mad.lo.u32 %1, bh, %4, %1;\n\t}"
+            : "+l"(lo64), "+r"(hi32) : "l"(a), "l"(b), "r"(one));
+#else
+    (void)one;
+    const bool lt = a < b;
+    const uint64_t v = lt ? a : b;
+    lo64 += (uint32_t)v; hi32 += (uint32_t)(v >> 32);
+    if (COUNT) cnt += lt ? 1u : 0u;
+#endif
+}
+
+
 // =============================================================================== the clean walker
 // The common case made cheap: the item bytes sb[ws..b) are all ACGT/acgt.  Anything else (a kept non-ACGT base, a
 // deleted byte) only sets a bit in `seen`; the function then returns false with acc untouched and the caller redoes
@@ -488,8 +510,12 @@ __host__ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ s
 //  - the van Herk buffers share ONE array: buf[i] holds the current block's scores below the running position and the
 //    previous block's suffix minima above it (the body is rotated so that the suffix pass follows element W-1);
 //  - checksums are plain wrapping 64-bit adds (2 instructions per value), the k-mer count is b - (ws + K - 1).
-template <int K, int M>
-__host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, Acc& acc) {
+//  - WARM: the K-1 warm-up bases are handed over as 2-bit codes in `wcodes` (find_ws_codes: code h = bits 2(K-2-h).., h = 0 the
+//    farthest) instead of bytes: lines of wrapped FASTA, whose warm-up crosses the previous line break.  `ws` is then the
+//    first byte of the item proper and every base of [ws,b) ends a k-mer.  (Round 2, measured: wrapped FASTA 75 -> 117 Gbases/s.)
+template <int K, int M, bool WARM>
+__host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, uint64_t wcodes, uint32_t one,
+                                                    Acc& acc) {
     static_assert(K >= 21 && K <= 31 && M >= 0 && M <= K, "clean walker shape (class bits 0..7 must not overlap the R insert)");
     constexpr bool MINI = M > 0;
     constexpr int W = MINI ? K - M + 1 : 1;
@@ -499,8 +525,12 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
     constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
     constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
+    constexpr bool V_PAIR = (NTG_WV & 1) != 0, V_CANON = (NTG_WV & 2) != 0, V_PRE = (NTG_WV & 4) != 0, V_SUF = (NTG_WV & 8) != 0,
+                   V_WIN = (NTG_WV & 16) != 0;
+    // checksums of this item: 64-bit sums of whole values or of their low words (s_k, s_m) plus 32-bit sums of high words
+    // (s_kh, s_mh; only needed mod 2^32):  sum = s + (sh << 32)  (mod 2^64)
     uint64_t f = 0, r = 0, s_k = 0, s_m = 0, pre = 0;
-    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
+    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu, s_kh = 0, s_mh = 0;
     uint64_t buf[W + 1];
 #pragma unroll
     for (int i = 0; i <= W; i++) buf[i] = 0;
@@ -536,16 +566,19 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
         const uint64_t y = r | LMASK;
         return lt62(x, y) ? x : y;
     };
-    auto tally = [&](uint64_t win) {
+    // canonical k-mer of this position (ties => was_rc = true, kmer.rs:124-128): returns the value to add to s_k (0 when the
+    // FMA-pipe form has accumulated it already)
+    auto canon = [&]() -> uint64_t {
         const uint64_t fm = f & KMASK;
-        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
-        s_k += lt ? fm : r;
+        if (V_CANON) { min62_accumulate_fma<true>(s_k, s_kh, n_nrc, fm, r, one); return 0; }
+        const bool lt = lt62(fm, r);
         n_nrc += lt ? 1u : 0u;
-        if (MINI) s_m += win;
+        return lt ? fm : r;
     };
     // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
     auto block = [&](auto check) {
         constexpr bool CHECK = decltype(check)::value;
+        uint64_t pend_k = 0, pend_m = 0;                       // first value of a pair of positions (3-input adds, V_PAIR)
 #pragma unroll
         for (int j = 0; j < B; j++) {
             if (CHECK && p + j >= b) return;
@@ -554,24 +587,44 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
             if (MINI) {
                 const uint64_t sc = score();
                 if (j == 0) {
-                    pre = (W == 1 || lt62(sc, pre)) ? sc : pre;
+                    if (W == 1) pre = sc; else min62_into<V_PRE>(pre, sc, one);
                     win = pre;
                     buf[W - 1] = sc;
 #pragma unroll
-                    for (int q = W - 2; q >= 1; q--) buf[q] = lt62(buf[q], buf[q + 1]) ? buf[q] : buf[q + 1];
+                    for (int q = W - 2; q >= 1; q--) min62_into<V_SUF>(buf[q], buf[q + 1], one);
                 } else {
                     const int i = j - 1;
-                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
-                    win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
+                    if (i == 0) pre = sc; else min62_into<V_PRE>(pre, sc, one);
+                    if (V_WIN) { uint32_t dummy = 0; min62_accumulate_fma<false>(s_m, s_mh, dummy, buf[i + 1], pre, one); }
+                    else win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
                     buf[i] = sc;
                 }
             }
-            tally(win);
+            const uint64_t ck = canon();
+            const bool FIRST = V_PAIR && !CHECK && (j & 1) == 0 && j + 1 < B;     // wait for the partner
+            const bool SECOND = V_PAIR && !CHECK && (j & 1) == 1;
+            if (FIRST) { pend_k = ck; pend_m = win; }
+            else if (SECOND) { if (!V_CANON) s_k = s_k + pend_k + ck; if (MINI) s_m = s_m + pend_m + win; }
+            else { if (!V_CANON) s_k += ck; if (MINI) s_m += win; }
         }
     };
 
     // head: K-1 bases that cannot end a k-mer — M-1 of them only feed F / R, the other W-1 are the first scores
-    {
+    if (WARM) {
+        (void)wcodes;
+#pragma unroll
+        for (int h = 0; h < K - 1; h++) {
+            const uint32_t code = (uint32_t)(wcodes >> (2 * (K - 2 - h))) & 3u;
+            f = (f << 2) | (uint64_t)code;
+            r = (r >> 2) | ((uint64_t)((3u - code) << (2 * (K - 1) - 32)) << 32);
+            if (MINI && h >= M - 1) {
+                const int i = h - (M - 1);
+                const uint64_t sc = score();
+                pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                buf[i] = sc;
+            }
+        }
+    } else {
         const int e0 = ws + (MINI ? M - 1 : K - 1), e1 = b < e0 ? b : e0;
 #pragma unroll 4
         for (; p < e1; p++) roll(p);
@@ -588,246 +641,19 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
             p += W - 1;
         }
     }
-    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
-    while (p + B <= b) { block(FalseT{}); p += B; if (NTG_BAIL_VOTE >= 2 && bail()) return false; }
+    if (bail()) return false;
+    while (p + B <= b) { block(FalseT{}); p += B; }
     if (p < b) block(TrueT{});
     if ((seen & 0x84u) || (RARE && rtop_min < RTOP_LIMIT)) return false;
-    const int nk_i = b - (ws + K - 1);
+    const int nk_i = WARM ? b - ws : b - (ws + K - 1);
     const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
     acc.n_kmers += nk; acc.n_not_rc += n_nrc;
-    acc.ksum_lo += s_k;
-    if (MINI) { acc.n_mini += nk; acc.msum += s_m; }
+    acc.ksum_lo += s_k + ((uint64_t)s_kh << 32);
+    if (MINI) { acc.n_mini += nk; acc.msum += s_m + ((uint64_t)s_mh << 32); }
     return true;
 }
 
-// walk_clean for an item whose warm-up is given as K-1 packed codes (find_ws_codes) instead of bytes (experiment NTG_WRAP=1):
-// lines of wrapped FASTA, whose warm-up crosses the previous line break.  Requires exactly K-1 warm-up bases.
-template <int K, int M>
-__host__ __device__ __forceinline__ bool walk_clean_w(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int a, int b, uint64_t wcodes, Acc& acc) {
-    static_assert(K >= 21 && K <= 31 && M >= 0 && M <= K, "clean walker shape (class bits 0..7 must not overlap the R insert)");
-    constexpr bool MINI = M > 0;
-    constexpr int W = MINI ? K - M + 1 : 1;
-    constexpr int B = MINI ? W : 8;                  // bases per unrolled block
-    constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
-    constexpr uint64_t MMASK = MINI ? ((1ull << (2 * M)) - 1) : 0, LMASK = MINI ? ((1ull << (2 * (K - M))) - 1) : 0;
-    constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
-    constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
-    constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
-    uint64_t f = 0, r = 0, s_k = 0, s_m = 0, pre = 0;
-    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
-    uint64_t buf[W + 1];
-#pragma unroll
-    for (int i = 0; i <= W; i++) buf[i] = 0;
-    int p = a;
-
-    // Leave as soon as a lane of the (converged part of the) warp has met a byte this walker cannot handle: the warp then
-    // redoes its items with walk_fast together instead of finishing a walk whose result is thrown away.  A hint only:
-    // exactness rests on each lane's own `seen` test at the end.
-    auto bail = [&]() -> bool {
-#if defined(__CUDA_ARCH__)
-        return __any_sync(__activemask(), (seen & 0x84u) != 0u);
-#else
-        return (seen & 0x84u) != 0u;
-#endif
-    };
-    auto roll = [&](int pp) {
-        const uint32_t u = comb[sb[pp]];
-        seen |= u;
-        f = (f << 2) | (uint64_t)(u & 3u);
-        r = (r >> 2) | ((uint64_t)(u & RMASK) << 32);
-    };
-    // score of the m-mer x ending here: min(x, RC_k(x)), RC_k(x) = R | LMASK (bitkmer.rs:146-162).  RC_k(x) can only be
-    // the smaller one when R < 4^M, i.e. when the last K-M bases are all T (4^-(K-M) per position in random sequence):
-    // RARE shapes take x and only remember the smallest top part of R seen; an item where that ever reached zero
-    // is handed to walk_fast like one with a non-ACGT base.
-    auto score = [&]() -> uint64_t {
-        const uint64_t x = f & MMASK;
-        if (RARE) {
-            const uint32_t top = (2 * M >= 32) ? (uint32_t)(r >> 32) : (uint32_t)(r >> (2 * M));
-            rtop_min = top < rtop_min ? top : rtop_min;
-            return x;
-        }
-        const uint64_t y = r | LMASK;
-        return lt62(x, y) ? x : y;
-    };
-    auto tally = [&](uint64_t win) {
-        const uint64_t fm = f & KMASK;
-        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
-        s_k += lt ? fm : r;
-        n_nrc += lt ? 1u : 0u;
-        if (MINI) s_m += win;
-    };
-    // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
-    auto block = [&](auto check) {
-        constexpr bool CHECK = decltype(check)::value;
-#pragma unroll
-        for (int j = 0; j < B; j++) {
-            if (CHECK && p + j >= b) return;
-            roll(p + j);
-            uint64_t win = 0;
-            if (MINI) {
-                const uint64_t sc = score();
-                if (j == 0) {
-                    pre = (W == 1 || lt62(sc, pre)) ? sc : pre;
-                    win = pre;
-                    buf[W - 1] = sc;
-#pragma unroll
-                    for (int q = W - 2; q >= 1; q--) buf[q] = lt62(buf[q], buf[q + 1]) ? buf[q] : buf[q + 1];
-                } else {
-                    const int i = j - 1;
-                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
-                    win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
-                    buf[i] = sc;
-                }
-            }
-            tally(win);
-        }
-    };
-
-    // head: the K-1 warm-up bases come from the register (code h = bits 2(K-2-h).., h = 0 the farthest); M-1 of them only feed
-    // F / R, the other W-1 are the first scores.  Every base of the item proper [a,b) then ends a k-mer.
-    {
-        auto roll_code = [&](uint32_t code) {
-            f = (f << 2) | (uint64_t)code;
-            r = (r >> 2) | ((uint64_t)((3u - code) << (2 * (K - 1) - 32)) << 32);
-        };
-#pragma unroll
-        for (int h = 0; h < K - 1; h++) {
-            roll_code((uint32_t)(wcodes >> (2 * (K - 2 - h))) & 3u);
-            if (MINI && h >= M - 1) {
-                const int i = h - (M - 1);
-                const uint64_t sc = score();
-                pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
-                buf[i] = sc;
-            }
-        }
-    }
-    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
-    while (p + B <= b) { block(FalseT{}); p += B; if (NTG_BAIL_VOTE >= 2 && bail()) return false; }
-    if (p < b) block(TrueT{});
-    if ((seen & 0x84u) || (RARE && rtop_min < RTOP_LIMIT)) return false;
-    const int nk_i = b - a;
-    const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
-    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
-    acc.ksum_lo += s_k;
-    if (MINI) { acc.n_mini += nk; acc.msum += s_m; }
-    return true;
-}
-
-
-// The same walk with the window minima on the FP64 pipe (experiment, NTG_FP64_MIN=1; measured in round 2): the three
-// 64-bit minima per base cost the INT pipe 2 SEL each on top of the DSETP; m-mer scores are below 2^42, so they can
-// live as exact doubles, min(a,b) = a - max(a-b,0) is three exact FP64 operations, and twice the sum of the window
-// minima accumulates exactly in a double.  The canonical k-mer part stays on integers (62 bits).
-template <int K, int M>
-__host__ __device__ __forceinline__ bool walk_clean_fp(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, Acc& acc) {
-    static_assert(K >= 21 && K <= 31 && M > 0 && M <= K && 2 * M <= 42 && (K - M) >= 8 && (K - M) <= 16, "FP64-minimum clean walker shape");
-    constexpr bool MINI = M > 0;
-    constexpr int W = MINI ? K - M + 1 : 1;
-    constexpr int B = MINI ? W : 8;                  // bases per unrolled block
-    constexpr uint64_t KMASK = (1ull << (2 * K)) - 1;
-    constexpr uint64_t MMASK = (1ull << (2 * M)) - 1;
-    constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
-    constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
-    uint64_t f = 0, r = 0, s_k = 0;
-    double pre = 0.0, s_m2 = 0.0;                    // s_m2: twice the sum of the window minima (exact: < 2^53, see the length guard)
-    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
-    double buf[W + 1];
-#pragma unroll
-    for (int i = 0; i <= W; i++) buf[i] = 0.0;
-    if (b - ws > 1000) return false;                 // 1000 * 2 * 4^M < 2^53 keeps every partial sum exact
-    int p = ws;
-
-    // Leave as soon as a lane of the (converged part of the) warp has met a byte this walker cannot handle: the warp then
-    // redoes its items with walk_fast together instead of finishing a walk whose result is thrown away.  A hint only:
-    // exactness rests on each lane's own `seen` test at the end.
-    auto bail = [&]() -> bool {
-#if defined(__CUDA_ARCH__)
-        return __any_sync(__activemask(), (seen & 0x84u) != 0u);
-#else
-        return (seen & 0x84u) != 0u;
-#endif
-    };
-    auto roll = [&](int pp) {
-        const uint32_t u = comb[sb[pp]];
-        seen |= u;
-        f = (f << 2) | (uint64_t)(u & 3u);
-        r = (r >> 2) | ((uint64_t)(u & RMASK) << 32);
-    };
-    // score of the m-mer x ending here as an exact double (x < 2^42): bit pattern 2^52 + x, minus 2^52.  RC_k(x) < x is
-    // the rare case of walk_clean (R < 4^M): remembered in rtop_min, the item then goes to walk_fast.
-    auto score = [&]() -> double {
-        const uint64_t x = f & MMASK;
-        const uint32_t top = (2 * M >= 32) ? (uint32_t)(r >> 32) : (uint32_t)(r >> (2 * M));
-        rtop_min = top < rtop_min ? top : rtop_min;
-        return u64_bits_as_double(0x4330000000000000ull | x) - 4503599627370496.0;
-    };
-    // min(a, b) of two integer-valued doubles below 2^52 with three FP64-pipe operations, all exact: a - max(a - b, 0)
-    auto dmin = [&](double a, double bb) -> double { const double t = a - bb; return fma(-0.5, t + fabs(t), a); };
-    auto tally = [&]() {
-        const uint64_t fm = f & KMASK;
-        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
-        s_k += lt ? fm : r;
-        n_nrc += lt ? 1u : 0u;
-    };
-    // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
-    auto block = [&](auto check) {
-        constexpr bool CHECK = decltype(check)::value;
-#pragma unroll
-        for (int j = 0; j < B; j++) {
-            if (CHECK && p + j >= b) return;
-            roll(p + j);
-            const double sc = score();
-            if (j == 0) {
-                pre = (W == 1) ? sc : dmin(sc, pre);
-                s_m2 = fma(2.0, pre, s_m2);
-                buf[W - 1] = sc;
-#pragma unroll
-                for (int q = W - 2; q >= 1; q--) buf[q] = dmin(buf[q], buf[q + 1]);
-            } else {
-                const int i = j - 1;
-                pre = (i == 0) ? sc : dmin(sc, pre);
-                const double u = buf[i + 1];
-                s_m2 += u + pre;                             // 2 min(u, pre) = (u + pre) - |u - pre|
-                s_m2 -= fabs(u - pre);
-                buf[i] = sc;
-            }
-            tally();
-        }
-    };
-
-    // head: K-1 bases that cannot end a k-mer — M-1 of them only feed F / R, the other W-1 are the first scores
-    {
-        const int e0 = ws + (MINI ? M - 1 : K - 1), e1 = b < e0 ? b : e0;
-#pragma unroll 4
-        for (; p < e1; p++) roll(p);
-        if (MINI) {
-#pragma unroll
-            for (int i = 0; i < W - 1; i++) {
-                if (p + i < b) {
-                    roll(p + i);
-                    const double sc = score();
-                    pre = (i == 0) ? sc : dmin(sc, pre);
-                    buf[i] = sc;
-                }
-            }
-            p += W - 1;
-        }
-    }
-    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
-    while (p + B <= b) { block(FalseT{}); p += B; if (NTG_BAIL_VOTE >= 2 && bail()) return false; }
-    if (p < b) block(TrueT{});
-    if ((seen & 0x84u) || rtop_min < RTOP_LIMIT) return false;
-    const int nk_i = b - (ws + K - 1);
-    const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
-    acc.n_kmers += nk; acc.n_not_rc += n_nrc;
-    acc.ksum_lo += s_k;
-    acc.n_mini += nk; acc.msum += (uint64_t)(s_m2 * 0.5);
-    return true;
-}
-
-
-// The clean walk for 33 <= K <= 63 (experiment NTG_CLEAN2=1, no minimizers: the reference's BitKmer is a u64): F and R are
+// The clean walk for 33 <= K <= 63 (round 2, measured: C5 shape 195 -> 400 Gbases/s; no minimizers: the reference's BitKmer is a u64): F and R are
 // 128-bit, the canonical k-mer is the smaller of the two as a 128-bit number (== the reference's lexicographic byte
 // compare, A<C<G<T), checksums are the wrapping sums of its low and high 64 bits.  Same contract as walk_clean: any byte
 // that is not ACGT/acgt makes it return false with acc untouched.  `comb2` = class bits | complement base pre-shifted for
@@ -875,7 +701,7 @@ __host__ __device__ __forceinline__ bool walk_clean2(const uint8_t* __restrict__
 #pragma unroll 4
         for (; p < e1; p++) roll(p);
     }
-    if (NTG_BAIL_VOTE >= 1 && bail()) return false;
+    if (bail()) return false;
     while (p + B <= b) {
 #pragma unroll
         for (int j = 0; j < B; j++) { roll(p + j); tally(); }
@@ -940,77 +766,6 @@ __device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uin
     return r;
 }
 
-// Wide look-back (the fused kernel): the CTAs of a persistent grid work on grid-many consecutive tiles at the same time, so
-// the tiles just before t only ever offer AGGREGATES until their own look-backs finish; with a 32-tile window the inclusive
-// prefix then crosses such a wave in grid/32 dependent hops (each: observe, load, reduce, publish - microseconds), and that
-// chain, not the walkers, set the time per wave.  Here lane l covers the G = ceil(grid/32) consecutive tiles
-// base - l*G - g (g = 0 nearest), so one step reaches back into the previous wave, whose inclusive prefixes were
-// published long ago: one hop per wave.  Flags are polled with relaxed loads (no L1 invalidation per poll); one
-// fence orders the payload loads, which bypass L1 (ld.global.cg).
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-    uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ SState ld_state_cg(const SState* p) {
-    static_assert(sizeof(SState) == 64, "four 16 B loads");
-    SState r;
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4* o = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; i++) o[i] = __ldcg(q + i);
-    return r;
-}
-__device__ __forceinline__ SState warp_lookback_wide(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, int G) {
-    SState suffix = identity_state();
-    int64_t base = (int64_t)t - 1;                                  // nearest predecessor not folded into `suffix` yet
-    uint32_t backoff = 32;
-    for (;;) {
-        const int64_t j0 = base - (int64_t)lane * G;                // this lane: tiles j0, j0-1, ..., j0-G+1
-        uint32_t stv[LB_GMAX];                                      // all flags of this lane in flight together
-#pragma unroll
-        for (int g = 0; g < LB_GMAX; g++) {
-            const int64_t j = j0 - g;
-            uint32_t st = 2;                                        // before the first tile: inclusive(identity)
-            if (g < G && j >= 0) { const uint32_t f = ld_relaxed_u32(&P.slots[j].flag); st = ((f >> 2) == epoch) ? (f & 3u) : 0u; }
-            stv[g] = st;
-        }
-        int g_inc = G, g_ready = 0;                                 // nearest g holding an inclusive prefix; leading published g's
-        bool open = true;
-#pragma unroll
-        for (int g = 0; g < LB_GMAX; g++) {
-            if (g < G && open) {
-                if (stv[g] == 0) open = false;
-                else { g_ready = g + 1; if (stv[g] == 2) { g_inc = g; open = false; } }
-            }
-        }
-        const bool has_inc = g_inc < G, complete = has_inc || g_ready == G;
-        const uint32_t inc_mask = __ballot_sync(0xffffffffu, has_inc), ok_mask = __ballot_sync(0xffffffffu, complete);
-        const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
-        const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if (~ok_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
-        __threadfence();                                            // flags observed -> payloads (acquire side)
-        SState acc = identity_state();                              // lanes beyond first_inc contribute the identity
-        if ((int)lane <= first_inc) {
-            const int gtop = ((int)lane == first_inc) ? g_inc : G - 1;
-            for (int g = gtop; g >= 0; g--) {                       // farthest (earliest) tile first
-                const int64_t j = j0 - g;
-                if (j < 0) continue;                                // (identity)
-                const SState sj = ld_state_cg(((int)lane == first_inc && g == g_inc) ? &P.slots[j].inc : &P.slots[j].agg);
-                acc = combine(acc, sj);
-            }
-        }
-        // ordered tree reduction: higher lanes hold EARLIER tiles; combine() is associative
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const SState earlier = shfl_state(acc, (int)lane + d < 32 ? (int)lane + d : (int)lane);
-            if ((int)lane + d < 32) acc = combine(earlier, acc);
-        }
-        acc = shfl_state(acc, 0);
-        suffix = combine(acc, suffix);
-        if (first_inc < 32) return suffix;
-        base -= 32 * (int64_t)G;
-    }
-}
-
 // =============================================================================== the kernel
 __device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
     // global position -> byte, from shared memory when resident, else from global memory
@@ -1027,21 +782,6 @@ template <int KW, bool MINI, int W>
 __device__ __noinline__ void walk_slow(const uint8_t* sb, const uint8_t* lut, int ws, int a, int b, const Params& P, Acc& acc, bool count_bases) {
     walk<KW, MINI, W>(sb, lut, ws, a, b, P, acc, count_bases);
 }
-#ifndef NTG_LB_WIDE
-#define NTG_LB_WIDE 0                                // 1: warp_lookback_wide (window 32 * NTGPU_LB_G tiles) instead of the 32-tile look-back.
-#endif                                               //    Measured slower (B200, C2: G=1 396, G=2 401-410, G=10 330 vs 425 Gbases/s): kept for A/B only
-#ifndef NTG_WRAP
-#define NTG_WRAP 0                                   // 1: walk_clean_w for items whose warm-up crosses deleted bytes (wrapped FASTA)
-#endif
-#ifndef NTG_CLEAN2
-#define NTG_CLEAN2 0                                 // 1: constant-folded two-word clean walker for k = 51 (walk_clean2)
-#endif
-#ifndef NTG_FP64_MIN
-#define NTG_FP64_MIN 0                               // 1: walk_clean_fp (window minima on the FP64 pipe) for the shapes it covers
-#endif
-#ifndef NTG_CLEAN
-#define NTG_CLEAN 1                                  // 0: items go straight to walk_fast (the round-1 kernel), for A/B timing
-#endif
 template <int K, int M>
 __device__ __noinline__ bool walk_fast_cold(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, int ws, int b, Acc& acc, uint32_t* seen_out) {
     FastLuts L{lut, rins, nullptr};
@@ -1056,50 +796,34 @@ __device__ __noinline__ bool walk_fast_cold(const uint8_t* sb, const uint8_t* lu
 // every warp would otherwise walk each item twice; a clean item puts the lane back.
 template <int KW, bool MINI, int W, int FK, int FM>
 __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, const uint32_t* comb, int a, int b, int lo,
-                                         bool lo_exact, const Params& P, Acc& acc, bool fasta, uint32_t& slow, uint32_t& mode) {
+                                         bool lo_exact, const Params& P, Acc& acc, bool fasta, uint32_t& slow, uint32_t& mode, uint32_t one) {
     if (b > a && sb[b - 1] == '\r') b--;                   // a trailing '\r' is deleted by normalize: nothing to walk
-    const bool had_cr_only = b <= a;
-    if (had_cr_only) return;
-#if NTG_WRAP
+    if (b <= a) return;
+    constexpr bool ONE = FK >= 21 && FK <= 31;              // constant-folded one-word shapes (clean / fast walkers)
     int got = 0; uint64_t wcodes = 0;
-    const int ws = find_ws_codes(sb, lut, a, lo, lo_exact, (int)P.k, slow, got, wcodes);
-    if (FK >= 21 && FK <= 31 && got == FK - 1 && a - ws != got && !__any_sync(__activemask(), mode != 0u)) {
-        // the warm-up crosses deleted bytes (wrapped FASTA: the previous line break): feed it from the register
-        if (walk_clean_w<(FK >= 21 && FK <= 31 ? FK : 21), (FK >= 21 && FK <= 31 ? FM : 0)>(sb, comb, a, b, wcodes, acc)) {
-            if (fasta) acc.n_bases += (uint64_t)(b - a);
-            return;
-        }
-    }
-#else
-    const int ws = find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
-#endif
-    if (FK > 32) {                                           // (NTG_CLEAN2 builds only instantiate this)
+    const int ws = ONE ? find_ws_codes(sb, lut, a, lo, lo_exact, (int)P.k, slow, got, wcodes) : find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
+    if (FK > 32) {
         if (!__any_sync(__activemask(), mode != 0u) && walk_clean2<(FK > 32 ? FK : 51)>(sb, comb, ws, b, acc)) return;
         mode = 1u;                                             // an item the clean walker refused: the warp's next item goes straight
         uint32_t any_bad = 0;                                  // to the generic walker, and comes back once an item was all ACGT
         for (int q = ws; q < b; q++) any_bad |= lut[sb[q]];
         if (any_bad <= 3u) mode = 0u;
         walk<KW, MINI, W>(sb, lut, ws, a, b, P, acc, fasta);
-    } else if (FK > 0) {
-        constexpr int CK = (FK > 0 && FK <= 32) ? FK : 21, CM = (FK > 0 && FK <= 32) ? FM : 0;
+    } else if (ONE) {
+        constexpr int CK = ONE ? FK : 21, CM = ONE ? FM : 0;
         bool done = false;
-        if (NTG_CLEAN && CK >= 21) {
-            if (!__any_sync(__activemask(), mode != 0u)) {
-                constexpr bool FP = NTG_FP64_MIN && CM > 0 && 2 * CM <= 42 && CK - CM >= 8 && CK - CM <= 16;
-                if (FP) done = walk_clean_fp<(FP ? CK : 31), (FP ? CM : 21)>(sb, comb, ws, b, acc);
-                else done = walk_clean<(CK >= 21 ? CK : 21), (CK >= 21 ? CM : 0)>(sb, comb, ws, b, acc);
-            }
-            if (!done) {
-                uint32_t seen = 0x80u;
-                done = walk_fast_cold<CK, CM>(sb, lut, rins, ws, b, acc, &seen);
-                mode = seen > 3u ? 1u : 0u;                 // (stays set when walk_fast gave up on a deleted byte)
-            }
-        } else {
-            FastLuts L{lut, rins, comb};
-            done = walk_fast<CK, CM>(sb, L, ws, b, acc);
+        if (!__any_sync(__activemask(), mode != 0u)) {
+            // a warm-up that crosses deleted bytes (wrapped FASTA: the previous line break) is fed from the register
+            if (got == CK - 1 && a - ws != got) done = walk_clean<CK, CM, true>(sb, comb, a, b, wcodes, one, acc);
+            else done = walk_clean<CK, CM, false>(sb, comb, ws, b, 0, one, acc);
+        }
+        if (!done) {
+            uint32_t seen = 0x80u;
+            done = walk_fast_cold<CK, CM>(sb, lut, rins, ws, b, acc, &seen);
+            mode = seen > 3u ? 1u : 0u;                     // (stays set when walk_fast gave up on a deleted byte)
         }
         if (done) {
-            if (fasta) acc.n_bases += (uint64_t)(b - a);   // no deleted bytes in [ws,b): every byte is a base
+            if (fasta) acc.n_bases += (uint64_t)(b - a);   // no deleted bytes in [a,b): every byte is a base
             return;
         }
         walk_slow<KW, MINI, W>(sb, lut, ws, a, b, P, acc, fasta);
@@ -1147,12 +871,6 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
 #define NTG_STATS 0                                  // 1: per-CTA cycle accounting into tallies[9..15] (ntg_tallies.reserved[2..6]):
 #endif                                               //    [9] sum of CTA lifetimes, [10] coordinator cycles inside look-backs, [11] look-backs,
                                                      //    [12] longest CTA lifetime, [14] thread 0 at the end-of-walk barrier, [15] thread 0 walking
-#ifndef NTG_TICKET
-#define NTG_TICKET 0                                 // 1: tiles are handed out by an atomic ticket instead of round-robin (A/B experiment)
-#endif
-#ifndef NTG_LB_DEFER
-#define NTG_LB_DEFER 1                               // 0: every tile's look-back is resolved inside its own tile (round-1 behaviour), for A/B timing
-#endif
 // Line events (fastq.rs:240-285) of line i < 4 of a tile, from global memory: start byte ('@' at role 0, '+' at role 2),
 // n_bases of a sequence line and the length check / n_records of a quality line that END in the tile.  `nl4` = the tile's
 // first four newline offsets (tile-relative), Cs = number of newlines in the tile, `pre` = the tile's exclusive prefix
@@ -1206,7 +924,11 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
     const uint64_t t = S.pend_t;
     const SState agg = S.pend_agg;
     SState pre = identity_state();
-    if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
+#ifdef NTG_EXP_NOLB                                  // TIMING EXPERIMENT ONLY (wrong results): what the look-back costs the tile loop
+    pre.count = S.pend_guess;
+    if (t + 1 == P.num_tiles && lane == 0) { SState inc = combine(pre, agg); inc.count = 4 * (P.n / 316); *P.final_state = inc; }
+#else
+    if (t > 0) pre = warp_lookback(P, t, epoch, lane);
     if (lane == 0) {
         const SState inc = combine(pre, agg);
         TileSlot* slot = &P.slots[t];
@@ -1215,6 +937,7 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
         st_release_u32(&slot->flag, epoch * 4 + 2);
         if (t + 1 == P.num_tiles) *P.final_state = inc;
     }
+#endif
     const uint32_t ord0 = (uint32_t)(pre.count & 3);
     if (S.pend_guess != ord0) slow |= FLAG_SPEC_MISS;
     const uint32_t Cs = S.pend_cs;
@@ -1226,44 +949,6 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
 }
 
 
-#if NTG_DC
-// Decoupled coordinator (experiment NTG_DC=1): consumes the per-tile records the walkers produce — look-back, inclusive
-// prefix, and either the prefix for walkers that wait for it or the check of the speculated phase plus the first four
-// lines' events (from global memory) — without ever joining a CTA barrier inside the tile loop.
-__device__ __noinline__ void dc_coordinator(const Params& P, Smem& S, uint32_t epoch, uint32_t lane, Acc& acc, uint32_t& slow) {
-    for (uint32_t seq = 0;; seq++) {
-        for (;;) {
-            if (S.dc_head > seq) break;
-            if (S.dc_total == seq) return;
-            __nanosleep(64);
-        }
-        __threadfence_block();
-        Smem::DcRec& rec = S.dc[seq % DC_R];
-        const uint64_t t = rec.t;
-        const SState agg = rec.agg;
-        SState pre = identity_state();
-        if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
-        if (lane == 0) {
-            const SState inc = combine(pre, agg);
-            TileSlot* slot = &P.slots[t];
-            slot->inc = inc;
-            __threadfence();
-            st_release_u32(&slot->flag, epoch * 4 + 2);
-            if (t + 1 == P.num_tiles) *P.final_state = inc;
-        }
-        if (rec.need_prefix) {
-            if (lane == 0) { rec.prefix = pre; __threadfence_block(); rec.prefix_ready = seq + 1; }
-        } else {
-            if (rec.guess != (uint32_t)(pre.count & 3)) slow |= FLAG_SPEC_MISS;
-            const uint32_t Cs = rec.cs;
-            if (lane < 4 && lane <= Cs)
-                first_lines_event(P.bytes, t * (uint64_t)P.tile_bytes, rec.nl4, Cs, rec.avail, rec.line0 != 0, pre, lane, acc, slow);
-        }
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); S.dc_tail = seq + 1; }
-    }
-}
-#endif
 
 template <int KW, bool MINI, int W, int FK, int FM>
 __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
@@ -1282,10 +967,6 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
     }
     if (tid == 0) {
         mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0;
-#if NTG_DC
-        S.dc_head = 0; S.dc_tail = 0; S.dc_total = 0xffffffffu;
-        for (int i = 0; i < DC_R; i++) S.dc[i].prefix_ready = 0;      // (shared memory is not zeroed: seq + 1 must never match by accident)
-#endif
     }
     __syncthreads();
     uint32_t parity = 0, slow = 0, my_seq = 0, mode = 0;
@@ -1300,39 +981,23 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
     const bool spec = P.spec != 0 && !fasta;          // walkers start on an inferred phase, the coordinator verifies it
     if (tid == 0) S.prefix_seq = 0;
 
-    uint32_t in_chunk = CHUNK;                     // position inside the claimed chunk (CHUNK = claim a new one)
-    uint64_t chunk_first = 0;
-#if NTG_DC
-    if (is_coord) dc_coordinator(P, S, epoch, lane, acc, slow);
-    else
-#endif
+    // Tiles are handed out by an atomic ticket (round 2, measured: C2 +2 %, C3 +57 % over static round-robin: with aggregates
+    // published early and the look-back deferred a late claimer no longer stalls its successors, and SMs that run ahead take
+    // more tiles instead of polling for slower predecessors).  Walker thread 0 claims the NEXT ticket when its own walk is
+    // done, so the atomic's latency hides behind the end-of-tile barrier.
+    if (tid == 0) { S.tile_idx_next = atomicAdd(ticket, 1u); S.one_word = P.one; }
+    __syncthreads();
+    uint32_t next_ticket = S.tile_idx_next;
+    const uint32_t one_r = *reinterpret_cast<volatile uint32_t*>(&S.one_word);
     for (;;) {
-        // Static round-robin tile assignment: CTA b takes tiles b, b + grid, b + 2 grid, ...  (No ticket: a tile that is
-        // claimed early but processed late publishes its aggregate late and stalls every look-back behind it; with the
-        // static order the next tile is known in advance, so it can be prefetched into L2 without being "claimed".)
-#if NTG_TICKET
-        // (experiment) dynamic order: the next unclaimed tile.  With the aggregate published early in the tile and the look-back
-        // deferred, a late claimer hurts less than in round 1, and SMs that run faster take more tiles instead of waiting.
-        if (tid == 0) S.tile_idx = atomicAdd(ticket, 1u);
-        tile_sync();
-        chunk_first = tile_begin + (uint64_t)S.tile_idx;
-#else
-        chunk_first = tile_begin + (uint64_t)blockIdx.x + (uint64_t)my_seq * gridDim.x;
-#endif
-        in_chunk = 0;
-        const uint64_t t = chunk_first + in_chunk;
+        const uint64_t t = tile_begin + (uint64_t)next_ticket;
         if (t >= tile_end) break;
-        const bool chained = in_chunk > 0;           // prefix = inclusive prefix of the tile this CTA just finished
-        in_chunk++;
         const uint32_t TB = P.tile_bytes;
         const uint64_t tile_start = t * (uint64_t)TB;
         const uint32_t avail = (uint32_t)min((uint64_t)TB, P.n - tile_start);
         const uint32_t halo = t > 0 ? HALO : 0;
         const uint32_t bulk = avail & ~15u;
 
-#if NTG_DC
-        if (tid == 0) while (my_seq - S.dc_tail >= (uint32_t)DC_R) __nanosleep(64);      // ring full: the coordinator is DC_R tiles behind
-#endif
         if (tid == 0) S.n_long = 0;
         // ---- P0: stage the tile (+ back halo) with one bulk async copy
         if (tid == 0 && halo + bulk) {
@@ -1355,10 +1020,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             if (tid < NTW && rowi < nrows) scan_row(reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW, lane, cnt[rd], wmask[rd]);
         }
         // ---- P2: ordered newline list (rows are ordered round-major: one scan of the packed per-round counts)
-        static_assert(MAXROUNDS == 2, "packed scan below assumes two rounds");
+        // The two per-round counts share one u32 for a single block scan: round 0 covers NTW rows (at most NTW * 256 = 73 728
+        // newlines: 17 bits), round 1 the remaining TILE / 256 - NTW rows (at most 12 288: 14 bits) -> 17 + 15 bits, no wrap
+        // even for a tile made of newlines (a run of blank lines is valid FASTA / FASTQ tail).
+        static_assert(MAXROUNDS == 2 && NTW * ROWB < (1 << 17) && (TILE / ROWB - NTW) * ROWB < (1 << 15), "packed scan: 17 + 15 bits");
         uint32_t Cpacked;
-        const uint32_t offp = block_excl_scan(cnt[0] | (cnt[1] << 16), &Cpacked, S.warp_tmp);
-        const uint32_t C0 = Cpacked & 0xFFFFu, C = C0 + (Cpacked >> 16);
+        const uint32_t offp = block_excl_scan(cnt[0] | (cnt[1] << 17), &Cpacked, S.warp_tmp);
+        const uint32_t C0 = Cpacked & 0x1FFFFu, C = C0 + (Cpacked >> 17);
         const bool overflow = C > NLMAX;
         if (overflow) slow |= FLAG_NL_OVERFLOW;
         if (!overflow) {
@@ -1367,7 +1035,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (!cnt[rd]) continue;
                 const uint32_t rowi = rd * NTW + tid;
                 const uint32_t* row = reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW;
-                uint32_t o = rd == 0 ? (offp & 0xFFFFu) : C0 + (offp >> 16);
+                uint32_t o = rd == 0 ? (offp & 0x1FFFFu) : C0 + (offp >> 17);
                 uint64_t mk = wmask[rd];
                 while (mk) {
                     const int jj = __ffsll((long long)mk) - 1;
@@ -1411,39 +1079,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         // skew between CTAs, and the end-of-tile barrier no longer waits for a look-back that has just begun), verifies
         // that tile's guess and does the events of its first four lines from global memory.
         const uint32_t guess = spec ? guess_phase(S.nl, sb, Cs, avail, line0_starts_here) : 4u;
-        const bool defer = !NTG_DC && NTG_LB_DEFER && spec && guess != 4u && t > 0;      // (tile 0 has nothing to look back at)
-#if NTG_DC
-        // Decoupled coordinator: walker thread 0 publishes the aggregate and hands the tile's record to the coordinator's ring.
-        const bool need_prefix = !spec || guess == 4u;            // the walkers of this tile wait for its prefix
-        if (tid == 0) {
-            SState agg = identity_state();
-            agg.count = C;
-            if (!overflow) for (uint32_t j = 0; j < 4 && j < C; j++) agg.last[j] = tile_start + S.nl[C - 1 - j];
-            if (fasta) {
-                agg.n_starts = nstarts_tot;
-                agg.first_nl = Cs ? tile_start + S.nl[0] : NONE;
-                if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
-            }
-            if (t > 0) {
-                TileSlot* slot = &P.slots[t];
-                slot->agg = agg;
-                __threadfence();
-                st_release_u32(&slot->flag, epoch * 4 + 1);
-            }
-            Smem::DcRec& rec = S.dc[my_seq % DC_R];
-            rec.agg = agg; rec.t = t; rec.guess = guess; rec.cs = Cs; rec.avail = avail; rec.line0 = line0_starts_here ? 1u : 0u;
-            rec.need_prefix = need_prefix ? 1u : 0u;
-            for (uint32_t j = 0; j < 4; j++) rec.nl4[j] = j < Cs ? S.nl[j] : 0u;
-            __threadfence_block();
-            S.dc_head = my_seq + 1;
-            const uint64_t tn = t + gridDim.x;                    // next tile of this CTA: pull it into L2
-            if (!NTG_TICKET && tn < tile_end) {
-                const uint64_t ns = tn * (uint64_t)TB;
-                const uint32_t nbytes = (uint32_t)min((uint64_t)TB, P.n - ns) & ~15u;
-                if (nbytes) bulk_prefetch_l2(P.bytes + ns, nbytes);
-            }
-        }
-#endif
+        const bool defer = spec && guess != 4u && t > 0;      // (tile 0 has nothing to look back at)
         SState pre = identity_state();
         if (is_coord) {
             SState agg = identity_state();
@@ -1455,7 +1091,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
             }
             TileSlot* slot = &P.slots[t];
-            if (t > 0 && !chained && lane == 0) {
+            if (t > 0 && lane == 0) {
                 slot->agg = agg;
                 __threadfence();
                 st_release_u32(&slot->flag, epoch * 4 + 1);
@@ -1478,15 +1114,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                     S.pend_valid = 1;
                 }
             } else {
-                if (chained) pre = S.last_inc;
-                else if (t > 0) pre = NTG_LB_WIDE ? warp_lookback_wide(P, t, epoch, lane, (int)P.lb_g) : warp_lookback(P, t, epoch, lane);
+                if (t > 0) pre = warp_lookback(P, t, epoch, lane);
                 if (lane == 0) {
                     const SState inc = combine(pre, agg);
                     slot->inc = inc;
                     __threadfence();
                     st_release_u32(&slot->flag, epoch * 4 + 2);
                     S.prefix = pre;
-                    S.last_inc = inc;
                     if (t + 1 == P.num_tiles) *P.final_state = inc;
                     __threadfence_block();
                     S.prefix_seq = my_seq + 1;
@@ -1495,28 +1129,10 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 #if NTG_STATS
             st_lb += clock64() - st_mark; if (!defer && t > 0) st_nlb++;
 #endif
-            if (lane == 0) {
-                // next tile of this CTA: pull it into L2 while the walkers work on this one
-                const uint64_t tn = t + gridDim.x;
-                if (!NTG_TICKET && tn < tile_end) {
-                    const uint64_t ns = tn * (uint64_t)TB;
-                    const uint32_t nbytes = (uint32_t)min((uint64_t)TB, P.n - ns) & ~15u;
-                    if (nbytes) bulk_prefetch_l2(P.bytes + ns, nbytes);
-                }
-            }
             __syncwarp();
         }
         bool have_pre = is_coord && !defer;
-#if NTG_DC
-        if (need_prefix) {                                        // FASTA / no unique local phase: wait for the coordinator
-            const Smem::DcRec& rec = S.dc[my_seq % DC_R];
-            while (rec.prefix_ready != my_seq + 1) __nanosleep(32);
-            __threadfence_block();
-            pre = rec.prefix; have_pre = true;
-        }
-#else
         if (!spec) { tile_sync(); pre = S.prefix; have_pre = true; }      // everyone needs the prefix before going on
-#endif
         // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
         auto prev_nl = [&](uint32_t i, uint32_t back) -> uint64_t {
             if (i >= back) return tile_start + S.nl[i - back];
@@ -1593,9 +1209,6 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             // and each walker takes the lines >= 4 of "its" record, whose previous newlines are all in the tile's list.
             if (!spec) { for (uint32_t i = tid; i <= Cs; i += NWK) line_events(i); }
             else if (is_coord && have_pre) { for (uint32_t i = lane; i <= Cs && i < 4; i += 32) line_events(i); }   // (deferred: resolve_pending)
-#if NTG_DC
-            else if (have_pre && tid < 4 && (uint32_t)tid <= Cs) line_events((uint32_t)tid);       // (the coordinator skips need_prefix tiles)
-#endif
             // (B) sequence lines only: walker thread j takes the j-th role-1 line of the tile (every 4th line)
             const uint32_t i_first = (1u - ord0) & 3u;
 #if NTG_STATS
@@ -1612,7 +1225,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                     if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                     int lo; bool lo_exact;
                     fastq_bound(i, a, lo, lo_exact);
-                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, false, slow, mode);
+                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, false, slow, mode, one_r);
                 }
             }
         } else {
@@ -1647,13 +1260,15 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                 int lo; bool lo_exact;
                 fasta_bound(i, a, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, true, slow, mode);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, true, slow, mode, one_r);
             }
         }
 #if NTG_STATS
         const long long st_done = clock64();
 #endif
+        if (tid == 0) S.tile_idx_next = atomicAdd(ticket, 1u);      // the next tile of this CTA (read after the barrier)
         tile_sync();
+        next_ticket = S.tile_idx_next;
 #if NTG_STATS
         if (!fasta && !is_coord) { st_walk += st_done - st_mark; st_wait += clock64() - st_done; }
 #endif
@@ -1681,17 +1296,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 const int a = la + (int)(pc - S.long_pref[j]) * PSEG, b = min(a + PSEG, lb);
                 int lo; bool lo_exact;
                 if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode, one_r);
             }
             tile_sync();                               // (no long lines: nothing read the tile since the barrier above, and
         }                                                  //  the reset of S.n_long at the next tile stores the value it holds)
         my_seq++;
     }
 
-#if NTG_DC
-    if (tid == 0) { __threadfence_block(); S.dc_total = my_seq; }
-#endif
-    if (!NTG_DC && is_coord && S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);      // the last deferred tile of this CTA
+    if (is_coord && S.pend_valid) resolve_pending(P, S, epoch, lane, acc, slow);      // the last deferred tile of this CTA
 
 #if NTG_STATS
     {

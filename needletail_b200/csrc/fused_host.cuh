@@ -1,7 +1,6 @@
 // fused_host.cuh — host orchestration of the fused tallies path.  Part of the unity build.
 #pragma once
 #include "fused.cuh"
-#include "fused_ws.cuh"
 #include "parse.cuh"
 
 struct FusedControl {           // device-resident control block, zeroed per call
@@ -27,22 +26,15 @@ struct FusedState {
     cudaEvent_t ev_chunk[FUSED_MAX_LAUNCHES] = {};
     uint8_t* feed_buf = nullptr; size_t feed_cap = 0;   // device staging for host feeds
     const uint8_t* host_bytes = nullptr;                // when the call was fed from host memory
-    bool used_ws = false;                               // the pending call ran the warp-specialised kernel
-    uint32_t general_tile_bytes = 0;                    // tile size for a re-run with the general kernel
-    int max_ctas_ws = 0;
+    uint32_t general_tile_bytes = 0;                    // tile size for a re-run without speculation
 };
 
 typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
 // kernel variants: three constant-folded headline shapes + the generic ones
-#if NTG_CLEAN2
-#define NTG_FUSED_KERNELS_X2(X) X((k_fused<2, false, 0, 51, 0>))
-#else
-#define NTG_FUSED_KERNELS_X2(X)
-#endif
 #define NTG_FUSED_KERNELS(X) \
     X((k_fused<1, true, 11, 31, 21>)) X((k_fused<1, true, 11, 21, 11>)) X((k_fused<1, false, 0, 31, 0>)) \
     X((k_fused<2, false, 0, 0, 0>)) X((k_fused<1, false, 0, 0, 0>)) X((k_fused<1, true, 11, 0, 0>)) X((k_fused<1, true, 0, 0, 0>)) \
-    NTG_FUSED_KERNELS_X2(X)
+    X((k_fused<2, false, 0, 51, 0>))
 static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) {
     using namespace fused;
     if (has_query) {                           // the query count lives in the generic walkers only
@@ -50,9 +42,7 @@ static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) 
         if (m == 0) return k_fused<1, false, 0, 0, 0>;
         return (k - m + 1 == 11) ? k_fused<1, true, 11, 0, 0> : k_fused<1, true, 0, 0, 0>;
     }
-#if NTG_CLEAN2
     if (k == 51 && m == 0) return k_fused<2, false, 0, 51, 0>;
-#endif
     if (k == 31 && m == 21) return k_fused<1, true, 11, 31, 21>;
     if (k == 21 && m == 11) return k_fused<1, true, 11, 21, 11>;
     if (k == 31 && m == 0) return k_fused<1, false, 0, 31, 0>;
@@ -60,15 +50,6 @@ static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) 
     if (m == 0) return k_fused<1, false, 0, 0, 0>;
     if (k - m + 1 == 11) return k_fused<1, true, 11, 0, 0>;
     return k_fused<1, true, 0, 0, 0>;
-}
-
-// warp-specialised kernel: FASTQ, constant-folded shapes, no query
-static fused_kernel_t pick_ws_kernel(uint32_t k, uint32_t m, bool has_query, int format) {
-    if (format != NTG_FMT_FASTQ || has_query) return nullptr;
-    if (k == 31 && m == 21) return fused_ws::k_fused_ws<31, 21>;
-    if (k == 21 && m == 11) return fused_ws::k_fused_ws<21, 11>;
-    if (k == 31 && m == 0) return fused_ws::k_fused_ws<31, 0>;
-    return nullptr;
 }
 
 static int fused_init(ntg_ctx* ctx) {
@@ -94,18 +75,7 @@ static int fused_init(ntg_ctx* ctx) {
         if (occ < 1) return ntg_set_error(ctx, NTG_ECUDA, "fused kernel does not fit on an SM");
         occ_min = occ < occ_min ? occ : occ_min;
     }
-    if (getenv("NTGPU_DEBUG")) fprintf(stderr, "[ntgpu] fused kernel occupancy: %d CTAs/SM\n", occ_min);
     st->max_ctas = occ_min * ctx->sm_count;     // persistent grid: every CTA resident (look-back needs forward progress)
-    fused_kernel_t wks[3] = {fused_ws::k_fused_ws<31, 21>, fused_ws::k_fused_ws<21, 11>, fused_ws::k_fused_ws<31, 0>};
-    int occ_ws = 1 << 30;
-    for (auto kf : wks) {
-        NTG_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fused_ws::SmemWS)));
-        int occ = 0;
-        NTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, fused_ws::WNT, sizeof(fused_ws::SmemWS)));
-        if (occ < 1) return ntg_set_error(ctx, NTG_ECUDA, "warp-specialised kernel does not fit on an SM");
-        occ_ws = occ < occ_ws ? occ : occ_ws;
-    }
-    st->max_ctas_ws = occ_ws * ctx->sm_count;
     return NTG_OK;
 }
 static void fused_destroy(ntg_ctx* ctx) {
@@ -153,13 +123,11 @@ static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
 }
 
 static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes,
-                       bool allow_ws = true) {
+                       bool allow_spec = true) {
     NTG_TRY(fused_init(ctx));
     FusedState* st = ctx->fused;
     if (st->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is already pending: collect it first");
     st->general_tile_bytes = tile_bytes;
-    st->used_ws = allow_ws && pick_ws_kernel(cfg->k, cfg->m, cfg->has_query != 0, format) != nullptr && getenv("NTGPU_WS") != nullptr;   // opt-in experiment
-    if (st->used_ws) tile_bytes = fused_ws::TB;
     if ((reinterpret_cast<uintptr_t>(dbytes) & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
     if (num_tiles > st->slots_cap) {
@@ -174,12 +142,7 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
     P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.ticket = nullptr;
     P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
-    P.spec = (allow_ws && format == NTG_FMT_FASTQ && getenv("NTGPU_NO_SPEC") == nullptr) ? 1 : 0;
-    {
-        const char* e = getenv("NTGPU_LB_G");                       // experiment knob: look-back window = 32 * G tiles
-        int g = e ? atoi(e) : 1;
-        P.lb_g = (uint32_t)(g < 1 ? 1 : (g > fused::LB_GMAX ? fused::LB_GMAX : g));
-    }
+    P.spec = (allow_spec && format == NTG_FMT_FASTQ && !(cfg->flags & NTG_TALLY_NO_SPECULATION)) ? 1 : 0;
     P.q_lo = P.q_hi = 0;
     if (cfg->has_query)
         for (uint32_t i = 0; i < cfg->k; i++) {
@@ -194,15 +157,7 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
 static int fused_launch(ntg_ctx* ctx, uint64_t tb, uint64_t te, int li) {
     FusedState* st = ctx->fused;
     if (te <= tb) return NTG_OK;
-    uint64_t nt = (te - tb + fused::CHUNK - 1) / fused::CHUNK;        // CTAs claim chunks of CHUNK consecutive tiles
-    if (st->used_ws) {
-        unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas_ws ? nt : (uint64_t)st->max_ctas_ws);
-        fused_kernel_t kf = pick_ws_kernel(st->P.k, st->P.m, st->P.has_query != 0, st->P.format);
-        kf<<<grid, fused_ws::WNT, sizeof(fused_ws::SmemWS), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
-        ctx->launches++;
-        NTG_CUDA(ctx, cudaGetLastError());
-        return NTG_OK;
-    }
+    uint64_t nt = te - tb;
     unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
     fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m, st->P.has_query != 0);
     kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
@@ -242,12 +197,11 @@ static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, f
     if (err) err->format = st->P.format;
     uint32_t fast_flags = st->h_ctrl->flags;
     if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
-    const uint32_t ws_flags = (st->used_ws || (fast_flags & fused::FLAG_SPEC_MISS)) ? fast_flags : 0;
-    if ((st->used_ws && (fast_flags & fused::FLAG_WS_BAIL)) || (fast_flags & fused::FLAG_SPEC_MISS)) {
-        // the warp-specialised kernel met something outside its remit, or a speculated FASTQ line phase was wrong:
-        // one plain pass (no speculation) of the general kernel over the same bytes
+    const uint32_t ws_flags = (fast_flags & fused::FLAG_SPEC_MISS) ? fast_flags : 0;
+    if (fast_flags & fused::FLAG_SPEC_MISS) {
+        // a speculated FASTQ line phase was wrong: one plain pass (no speculation) over the same bytes
         const ntg_tally_config cfg = st->cfg;
-        NTG_TRY(fused_begin(ctx, st->P.bytes, st->P.n, st->P.format, &cfg, st->general_tile_bytes, /*allow_ws=*/false));
+        NTG_TRY(fused_begin(ctx, st->P.bytes, st->P.n, st->P.format, &cfg, st->general_tile_bytes, /*allow_spec=*/false));
         int s2 = fused_launch(ctx, 0, st->P.num_tiles, 0);
         if (s2 == NTG_OK) s2 = fused_finish_enqueue(ctx);
         st->pending = false;

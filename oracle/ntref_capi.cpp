@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <sched.h>
 #include <thread>
 
 using namespace ntref;
@@ -183,17 +184,39 @@ static void tally_fastq_stream(const uint8_t* buf, size_t n, unsigned k, unsigne
 // Returns elapsed seconds (steady_clock around the parallel region).
 double ntref_bench_fastq(const uint8_t* buf, const uint64_t* offs, unsigned nthreads, unsigned k, unsigned m,
                          int iupac, uint64_t* out) {
-    std::vector<Tallies> parts(nthreads);
-    auto t0 = std::chrono::steady_clock::now();
+    // Each thread tallies into its OWN stack-local Tallies (the per-k-mer increments must not share cache lines
+    // between threads) and publishes it once at the end; the threads are created and parked on a start gate
+    // before the clock starts, so thread creation is not timed.
+    struct alignas(128) Slot { Tallies t; };
+    std::vector<Slot> parts(nthreads);
+    std::atomic<unsigned> ready{0};
+    std::atomic<bool> go{false};
     std::vector<std::thread> th;
     for (unsigned i = 0; i < nthreads; i++)
-        th.emplace_back([&, i] { tally_fastq_stream(buf + offs[i], offs[i + 1] - offs[i], k, m, iupac, parts[i]); });
+        th.emplace_back([&, i] {
+            Tallies local;
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+            tally_fastq_stream(buf + offs[i], offs[i + 1] - offs[i], k, m, iupac, local);
+            parts[i].t = local;
+        });
+    while (ready.load() < nthreads) std::this_thread::yield();
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
     for (auto& x : th) x.join();
     auto t1 = std::chrono::steady_clock::now();
     Tallies t;
-    for (auto& p : parts) t.add(p);
+    for (auto& p : parts) t.add(p.t);
     store_tallies(t, out);
     return std::chrono::duration<double>(t1 - t0).count();
+}
+// Host threads this process may actually run on (cgroup / affinity mask), not the machine's core count.
+unsigned ntref_usable_cores(void) {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) { int c = CPU_COUNT(&set); if (c > 0) return (unsigned)c; }
+    unsigned h = std::thread::hardware_concurrency();
+    return h ? h : 1;
 }
 
 // Synthetic generator (CPU side), multi-threaded over records.

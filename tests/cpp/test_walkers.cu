@@ -39,7 +39,7 @@ static bool same(const Acc& a, const ntref::Tallies& t, bool mini) {
            (!mini || (a.n_mini == t.n_minimizers && a.msum == t.minimizer_sum));
 }
 
-enum Which { CLEAN = 1, FAST = 2, GENERIC = 4, CLEANFP = 8 };   // CLEANFP: walk_clean_fp (the NTG_FP64_MIN experiment) in place of walk_clean
+enum Which { CLEAN = 1, FAST = 2, GENERIC = 4 };
 // the kernel's run_item chain on sb[a..b) with warm-up not below lo; `which` selects the walkers that may be used
 template <int K, int M>
 static bool item(const uint8_t* sb, const Luts& L, int a, int b, int lo, int which, Acc& acc, int* used = nullptr) {
@@ -48,10 +48,7 @@ static bool item(const uint8_t* sb, const Luts& L, int a, int b, int lo, int whi
     if (b <= a) return true;
     uint32_t slow = 0;
     const int ws = fused::find_ws(sb, g_cls, a, lo, true, K, slow);
-    if ((which & CLEAN) && fused::walk_clean<K, M>(sb, L.comb, ws, b, acc)) { if (used) *used = CLEAN; return true; }
-    if constexpr (M > 0 && 2 * M <= 42 && K - M >= 8 && K - M <= 16) {
-        if ((which & CLEANFP) && fused::walk_clean_fp<K, M>(sb, L.comb, ws, b, acc)) { if (used) *used = CLEANFP; return true; }
-    }
+    if ((which & CLEAN) && fused::walk_clean<K, M, false>(sb, L.comb, ws, b, 0, 1u, acc)) { if (used) *used = CLEAN; return true; }
     fused::FastLuts FL{g_cls, L.rins, L.comb};
     if ((which & FAST) && fused::walk_fast<K, M>(sb, FL, ws, b, acc)) { if (used) *used = FAST; return true; }
     if (which & GENERIC) {
@@ -86,10 +83,10 @@ static int run(std::mt19937_64& rng, int iters, const char* name) {
         ntref::Tallies t;
         ntref::tally_sequence(sb, (size_t)n, K, M, false, nullptr, t, norm, rc);
         // 1. whole item through every admissible chain
-        for (int which : std::vector<int>{CLEAN | FAST | GENERIC, CLEANFP | FAST | GENERIC, FAST | GENERIC, GENERIC}) {
+        for (int which : std::vector<int>{CLEAN | FAST | GENERIC, FAST | GENERIC, GENERIC}) {
             Acc acc; int used = 0;
             item<K, M>(sb, L, 0, n, 0, which, acc, &used);
-            if (which == (CLEAN | FAST | GENERIC) || used == CLEANFP) used_cnt[used]++;
+            if (which == (CLEAN | FAST | GENERIC)) used_cnt[used]++;
             if (!same(acc, t, M > 0)) {
                 std::printf("%s: whole item mismatch (chain %d, walker %d) n=%d: kmers %llu/%llu not_rc %llu/%llu ksum %llx/%llx mini %llu/%llu msum %llx/%llx\n  %s\n",
                             name, which, used, n, (unsigned long long)acc.n_kmers, (unsigned long long)t.n_kmers, (unsigned long long)acc.n_not_rc,
@@ -102,7 +99,7 @@ static int run(std::mt19937_64& rng, int iters, const char* name) {
         if (n >= 2) {
             int c1 = (int)(rng() % (unsigned)n), c2 = (int)(rng() % (unsigned)n);
             if (c1 > c2) std::swap(c1, c2);
-            for (int which : std::vector<int>{CLEAN | FAST | GENERIC, CLEANFP | FAST | GENERIC, GENERIC}) {
+            for (int which : std::vector<int>{CLEAN | FAST | GENERIC, GENERIC}) {
                 Acc acc;
                 // (a '\r' ending a fragment is a deleted byte wherever it is: run_item's trim is harmless for inner fragments)
                 auto frag = [&](int a, int b, bool) { if (b > a) item<K, M>(sb, L, a, b, 0, which, acc); };
@@ -111,7 +108,7 @@ static int run(std::mt19937_64& rng, int iters, const char* name) {
             }
         }
     }
-    std::printf("%s: %d items, walker used: clean %ld (fp variant %ld), fast %ld, generic %ld; %s\n", name, iters, used_cnt[CLEAN], used_cnt[CLEANFP],
+    std::printf("%s: %d items, walker used: clean %ld, fast %ld, generic %ld; %s\n", name, iters, used_cnt[CLEAN],
                 used_cnt[FAST], used_cnt[GENERIC], fails ? "FAIL" : "ok");
     return fails;
 }
@@ -260,7 +257,7 @@ static int run2(std::mt19937_64& rng, int iters, const char* name) {
     return fails;
 }
 
-// wrapped sequences: items are the lines; a line's warm-up crosses the previous line break and is fed to walk_clean_w as codes
+// wrapped sequences: items are the lines; a line's warm-up crosses the previous line break and is fed to walk_clean<WARM> as codes
 template <int K, int M>
 static int run_wrapped(std::mt19937_64& rng, int iters, const char* name) {
     const Luts L = make_luts<K>();
@@ -289,7 +286,7 @@ static int run_wrapped(std::mt19937_64& rng, int iters, const char* name) {
             if (b <= a) continue;
             uint32_t slow = 0; int got = 0; uint64_t wcodes = 0;
             const int ws = fused::find_ws_codes(sb, g_cls, a, 0, true, K, slow, got, wcodes);
-            if (got == K - 1 && a - ws != got && fused::walk_clean_w<K, M>(sb, L.comb, a, b, wcodes, acc)) { n_w++; continue; }
+            if (got == K - 1 && a - ws != got && fused::walk_clean<K, M, true>(sb, L.comb, a, b, wcodes, 1u, acc)) { n_w++; continue; }
             n_other++;
             item<K, M>(sb, L, a, b, 0, CLEAN | FAST | GENERIC, acc);
         }
@@ -300,7 +297,7 @@ static int run_wrapped(std::mt19937_64& rng, int iters, const char* name) {
             fails++;
         }
     }
-    std::printf("%s wrapped: %d sequences, %ld lines through walk_clean_w, %ld through the other walkers; %s\n", name, iters, n_w, n_other, fails ? "FAIL" : "ok");
+    std::printf("%s wrapped: %d sequences, %ld lines through walk_clean<WARM>, %ld through the other walkers; %s\n", name, iters, n_w, n_other, fails ? "FAIL" : "ok");
     return fails;
 }
 

@@ -26,13 +26,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libntgpu.so does not export {n}"
     assert sorted(lib._declared) == names          # the ctypes face covers the whole header
-    assert lib.ntg_abi_version() == 1
+    assert lib.ntg_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     import needletail_b200 as nt
     assert C.sizeof(nt._Record) == 80 and C.sizeof(nt._Tallies) == 128
-    assert C.sizeof(nt._TallyConfig) == 80 and C.sizeof(nt._ParseError) == 264
+    assert C.sizeof(nt._TallyConfig) == 84 and C.sizeof(nt._ParseError) == 264
 
 
 def test_no_cpu_fallback():
@@ -203,10 +203,10 @@ def test_record_from_table_row():
 
 
 def test_experiment_builds_compile(tmp_path):
-    """The compile-time A/B experiments of fused.cuh (tools/ab_variants.sh) stay buildable: one nvcc pass with all of them on."""
+    """The diagnostic build (-DNTG_STATS=1: per-CTA cycle accounting) stays buildable."""
     import shutil
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    flags = ["-DNTG_FP64_MIN=1", "-DNTG_TICKET=1", "-DNTG_DC=1", "-DNTG_STATS=1", "-DNTG_CLEAN2=1", "-DNTG_WRAP=1", "-DNTG_LB_WIDE=1"]
+    flags = ["-DNTG_STATS=1"]
     out = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr", *flags, "-cubin",
                           "-o", str(tmp_path / "all_on.cubin"), os.path.join(ROOT, "needletail_b200", "csrc", "ntgpu.cu")],
                          capture_output=True, text=True, timeout=900)
