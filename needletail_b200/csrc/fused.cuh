@@ -83,7 +83,10 @@ struct Params {
     const uint8_t* bytes;
     uint64_t n;
     uint64_t num_tiles;
-    TileSlot* slots;
+    TileSlot* slots;                   // ring of 1 << slot_shift tile slots (tile t uses slot t & slot_mask, generation t >> slot_shift)
+    unsigned long long* cw;            // FASTQ: one 64-bit look-back word per tile, same ring (see fastq_lookback)
+    uint32_t slot_mask, slot_shift;
+    uint64_t gmin;                     // lowest global byte position that is addressable through `bytes` in this launch (streamed rings)
     uint32_t* ticket;
     unsigned long long* tallies;      // 16 x u64
     uint32_t* flags;
@@ -150,7 +153,7 @@ struct __align__(16) Smem {
     uint32_t rins[256];                // fast walker: complement base pre-shifted into the high word of R
     uint32_t comb[256];                // clean walker: lut | rins in one word
     uint64_t bar;
-    uint32_t warp_tmp[NT / 32 + 2];
+    uint32_t warp_tmp[4][NT / 32 + 2];  // one array per block-scan call site (the scans use a single barrier)
     uint64_t red[NT / 32][9];
     SState prefix;                     // exclusive prefix of this tile
     volatile uint32_t prefix_seq;      // number of tiles of this CTA whose prefix has been resolved by the coordinator
@@ -160,7 +163,6 @@ struct __align__(16) Smem {
     uint32_t pend_guess, pend_cs, pend_avail, pend_line0;
     uint32_t pend_nl4[4];              // the tile's first four newline offsets
     volatile uint32_t pend_valid;
-    uint32_t one_word;                 // == 1: read back into a (non-uniform) register, the multiplier of the FMA-pipe moves
     uint32_t tile_idx_next;            // ticket of this CTA's next tile, claimed by walker thread 0 at the end of its walk
     uint32_t n_long;
     uint32_t long_line[LONGMAX];       // line indices of long sequence lines
@@ -170,32 +172,39 @@ struct __align__(16) Smem {
 
 // barrier of the threads that run the tile loop (all of the CTA, or the walkers only when the coordinator is decoupled)
 __device__ __forceinline__ void tile_sync() { __syncthreads(); }
+// Block-wide scans with ONE barrier (round 2: the serial fold by thread 0 between two more barriers held 4.7 % of the stall
+// samples): warp scans by shuffle, the warp totals go through shared memory, every warp folds the totals of the warps
+// before it itself.  `tmp` must not be written again before another CTA barrier: every call site has its own array.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* tmp) {
     constexpr int NW = NWK / 32;
-    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
+    static_assert(NW <= 16, "the warp totals are folded by one 16-lane shuffle scan");
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
     if (lane == 31) tmp[w] = inc;
     tile_sync();
-    if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NW; i++) { uint32_t t = tmp[i]; tmp[i] = s; s += t; } tmp[NW] = s; }
-    tile_sync();
-    uint32_t r = inc - v + tmp[w];
-    *total = tmp[NW];
-    tile_sync();
-    return r;
+    const uint32_t x = lane < NW ? tmp[lane] : 0u;
+    uint32_t xi = x;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+    *total = __shfl_sync(0xffffffffu, xi, NW - 1);
+    return inc - v + __shfl_sync(0xffffffffu, xi - x, w);
 }
 __device__ __forceinline__ uint32_t block_incl_max(uint32_t v, uint32_t* tmp) {   // inclusive max-scan across threads
     constexpr int NW = NWK / 32;
-    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = v;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, t); }
     if (lane == 31) tmp[w] = inc;
     tile_sync();
-    if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NW; i++) { uint32_t t = tmp[i]; tmp[i] = s; s = max(s, t); } }
-    tile_sync();
-    uint32_t r = max(inc, tmp[w]);
-    tile_sync();
-    return r;
+    const uint32_t x = lane < NW ? tmp[lane] : 0u;
+    uint32_t xi = x;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi = max(xi, t); }
+    const uint32_t before = __shfl_sync(0xffffffffu, xi, w ? w - 1 : 0);           // max over the warps before w
+    return w ? max(inc, before) : inc;
 }
 
 // ---- P1 helper: newlines of one 256 B row ---------------------------------------------------
@@ -450,55 +459,11 @@ __host__ __device__ __forceinline__ bool walk_fast(const uint8_t* __restrict__ s
 }
 
 
-// ---- pipe-balancing helpers (round 2).  Measured on B200 (tools/ubench/pipes.cu, profiles/r2a_*): SEL, FSEL, LOP3, SHF, IADD3,
-// PRMT, VIMNMX and ISETP all issue on the ALU pipe (2 cycles per warp instruction), IMAD / IMAD.WIDE / IMAD.MOV on the FMA pipe
-// (2 cycles), DSETP on the FP64 pipe (~4.5 cycles); instructions of different pipes overlap (pairs cost ~2.05 cycles).  The
-// clean walker's main loop was 19 ALU : 7 FMA instructions per base, i.e. ALU-pipe bound.  A 64-bit select is two SELs (ALU);
-// the same effect is had on the FMA pipe with two PREDICATED multiply-adds by a run-time 1 (`one`, which ptxas cannot fold
-// into a SEL): a conditional move "@p d = s * one + 0", or a conditional accumulate "@p acc += s * one".
-#ifndef NTG_WV
-#define NTG_WV 0                                     // bit 0 pairwise 3-input checksum adds, bit 1 canonical pick accumulated on the FMA pipe,
-#endif                                               // bit 2 prefix minimum, bit 3 suffix pass, bit 4 window pick on the FMA pipe
-// dst = min(dst, src), both below 2^62
-template <bool FMA>
-__host__ __device__ __forceinline__ void min62_into(uint64_t& dst, uint64_t src, uint32_t one) {
-#ifdef __CUDA_ARCH__
-    if (FMA) {
-        asm("{\n\t.reg .pred p;\n\t.reg .f64 a, b;\n\t.reg .u32 dl, dh, sl, sh;\n\t"
-            "mov.b64 a, %0;\n\tmov.b64 b, %1;\n\tmov.b64 {dl, dh}, %0;\n\tmov.b64 {sl, sh}, %1;\n\t"
-            "setp.lt.f64 p, b, a;\n\t@p mad.lo.u32 dl, sl, %2, 0;\n\t@p mad.lo.u32 dh, sh, %2, 0;\n\t"
-            "mov.b64 %0, {dl, dh};\n\t}" : "+l"(dst) : "l"(src), "r"(one));
-        return;
-    }
-#endif
-    (void)one;
-    dst = lt62(src, dst) ? src : dst;
-}
-// lo64 += low word of min(a, b); hi32 += its high word; cnt += (a < b)   (a, b below 2^62; COUNT = false leaves cnt alone)
-template <bool COUNT>
-__host__ __device__ __forceinline__ void min62_accumulate_fma(uint64_t& lo64, uint32_t& hi32, uint32_t& cnt, uint64_t a, uint64_t b, uint32_t one) {
-#ifdef __CUDA_ARCH__
-    if (COUNT)
-        asm("{\n\t.reg .pred p;\n\t.reg .f64 x, y;\n\t.reg .u32 al, ah, bl, bh;\n\t"
-            "mov.b64 x, %3;\n\tmov.b64 y, %4;\n\tmov.b64 {al, ah}, %3;\n\tmov.b64 {bl, bh}, %4;\n\t"
-            "setp.lt.f64 p, x, y;\n\t@p mad.wide.u32 %0, al, %5, %0;\n\t@!p mad.wide.u32 %0, bl, %5, %0;\n\t"
-            "@p mad.lo.u32 %1, ah, %5, %1;\n\t@!p mad.lo.u32 %1, bh, %5, %1;\n\t@p mad.lo.u32 %2, %5, %5, %2;\n\t}"
-            : "+l"(lo64), "+r"(hi32), "+r"(cnt) : "l"(a), "l"(b), "r"(one));
-    else
-        asm("{\n\t.reg .pred p;\n\t.reg .f64 x, y;\n\t.reg .u32 al, ah, bl, bh;\n\t"
-            "mov.b64 x, %2;\n\tmov.b64 y, %3;\n\tmov.b64 {al, ah}, %2;\n\tmov.b64 {bl, bh}, %3;\n\t"
-            "setp.lt.f64 p, x, y;\n\t@p mad.wide.u32 %0, al, %4, %0;\n\t@!p mad.wide.u32 %0, bl, %4, %0;\n\t"
-            "@p mad.lo.u32 %1, ah, %4, %1;\n\t@!p mad.lo.u32 %1, bh, %4, %1;\n\t}"
-            : "+l"(lo64), "+r"(hi32) : "l"(a), "l"(b), "r"(one));
-#else
-    (void)one;
-    const bool lt = a < b;
-    const uint64_t v = lt ? a : b;
-    lo64 += (uint32_t)v; hi32 += (uint32_t)(v >> 32);
-    if (COUNT) cnt += lt ? 1u : 0u;
-#endif
-}
-
+// (Round 2, measured on B200 with tools/ubench/pipes.cu, profiles/r2a_*: SEL, FSEL, LOP3, SHF, IADD3, PRMT, VIMNMX and ISETP all
+// issue on the ALU pipe at 2 cycles per warp instruction, IMAD / IMAD.WIDE / IMAD.MOV on the FMA pipe at 2 cycles, DSETP at
+// ~4.5 cycles on the FP64 pipe.  Moving the 64-bit selects of the window minima to the FMA pipe as predicated multiply-adds
+// by a run-time 1 was tried (NTG_WV builds, profiles/r2b_*): ptxas folds most of them back into SEL or adds register moves;
+// 462 -> 450..462 Gbases/s.  Dropped.)
 
 // =============================================================================== the clean walker
 // The common case made cheap: the item bytes sb[ws..b) are all ACGT/acgt.  Anything else (a kept non-ACGT base, a
@@ -514,8 +479,7 @@ __host__ __device__ __forceinline__ void min62_accumulate_fma(uint64_t& lo64, ui
 //    farthest) instead of bytes: lines of wrapped FASTA, whose warm-up crosses the previous line break.  `ws` is then the
 //    first byte of the item proper and every base of [ws,b) ends a k-mer.  (Round 2, measured: wrapped FASTA 75 -> 117 Gbases/s.)
 template <int K, int M, bool WARM>
-__host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, uint64_t wcodes, uint32_t one,
-                                                    Acc& acc) {
+__host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ sb, const uint32_t* __restrict__ comb, int ws, int b, uint64_t wcodes, Acc& acc) {
     static_assert(K >= 21 && K <= 31 && M >= 0 && M <= K, "clean walker shape (class bits 0..7 must not overlap the R insert)");
     constexpr bool MINI = M > 0;
     constexpr int W = MINI ? K - M + 1 : 1;
@@ -525,12 +489,8 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
     constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
     constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
-    constexpr bool V_PAIR = (NTG_WV & 1) != 0, V_CANON = (NTG_WV & 2) != 0, V_PRE = (NTG_WV & 4) != 0, V_SUF = (NTG_WV & 8) != 0,
-                   V_WIN = (NTG_WV & 16) != 0;
-    // checksums of this item: 64-bit sums of whole values or of their low words (s_k, s_m) plus 32-bit sums of high words
-    // (s_kh, s_mh; only needed mod 2^32):  sum = s + (sh << 32)  (mod 2^64)
     uint64_t f = 0, r = 0, s_k = 0, s_m = 0, pre = 0;
-    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu, s_kh = 0, s_mh = 0;
+    uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
     uint64_t buf[W + 1];
 #pragma unroll
     for (int i = 0; i <= W; i++) buf[i] = 0;
@@ -566,19 +526,16 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
         const uint64_t y = r | LMASK;
         return lt62(x, y) ? x : y;
     };
-    // canonical k-mer of this position (ties => was_rc = true, kmer.rs:124-128): returns the value to add to s_k (0 when the
-    // FMA-pipe form has accumulated it already)
-    auto canon = [&]() -> uint64_t {
+    auto tally = [&](uint64_t win) {
         const uint64_t fm = f & KMASK;
-        if (V_CANON) { min62_accumulate_fma<true>(s_k, s_kh, n_nrc, fm, r, one); return 0; }
-        const bool lt = lt62(fm, r);
+        const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
+        s_k += lt ? fm : r;
         n_nrc += lt ? 1u : 0u;
-        return lt ? fm : r;
+        if (MINI) s_m += win;
     };
     // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
     auto block = [&](auto check) {
         constexpr bool CHECK = decltype(check)::value;
-        uint64_t pend_k = 0, pend_m = 0;                       // first value of a pair of positions (3-input adds, V_PAIR)
 #pragma unroll
         for (int j = 0; j < B; j++) {
             if (CHECK && p + j >= b) return;
@@ -587,25 +544,19 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
             if (MINI) {
                 const uint64_t sc = score();
                 if (j == 0) {
-                    if (W == 1) pre = sc; else min62_into<V_PRE>(pre, sc, one);
+                    pre = (W == 1 || lt62(sc, pre)) ? sc : pre;
                     win = pre;
                     buf[W - 1] = sc;
 #pragma unroll
-                    for (int q = W - 2; q >= 1; q--) min62_into<V_SUF>(buf[q], buf[q + 1], one);
+                    for (int q = W - 2; q >= 1; q--) buf[q] = lt62(buf[q], buf[q + 1]) ? buf[q] : buf[q + 1];
                 } else {
                     const int i = j - 1;
-                    if (i == 0) pre = sc; else min62_into<V_PRE>(pre, sc, one);
-                    if (V_WIN) { uint32_t dummy = 0; min62_accumulate_fma<false>(s_m, s_mh, dummy, buf[i + 1], pre, one); }
-                    else win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
+                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                    win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
                     buf[i] = sc;
                 }
             }
-            const uint64_t ck = canon();
-            const bool FIRST = V_PAIR && !CHECK && (j & 1) == 0 && j + 1 < B;     // wait for the partner
-            const bool SECOND = V_PAIR && !CHECK && (j & 1) == 1;
-            if (FIRST) { pend_k = ck; pend_m = win; }
-            else if (SECOND) { if (!V_CANON) s_k = s_k + pend_k + ck; if (MINI) s_m = s_m + pend_m + win; }
-            else { if (!V_CANON) s_k += ck; if (MINI) s_m += win; }
+            tally(win);
         }
     };
 
@@ -648,8 +599,8 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     const int nk_i = WARM ? b - ws : b - (ws + K - 1);
     const uint64_t nk = nk_i > 0 ? (uint64_t)nk_i : 0;
     acc.n_kmers += nk; acc.n_not_rc += n_nrc;
-    acc.ksum_lo += s_k + ((uint64_t)s_kh << 32);
-    if (MINI) { acc.n_mini += nk; acc.msum += s_m + ((uint64_t)s_mh << 32); }
+    acc.ksum_lo += s_k;
+    if (MINI) { acc.n_mini += nk; acc.msum += s_m; }
     return true;
 }
 
@@ -727,27 +678,30 @@ __device__ __forceinline__ SState shfl_state(const SState& v, int src) {
     r.first_nl = __shfl_sync(0xffffffffu, v.first_nl, src);
     return r;
 }
-// Exclusive prefix of tile t, computed by one whole warp: lane l inspects tile base-l, so 32 predecessors
-// are examined per step (a serial walk makes look-backs slow, which lengthens the window of tiles that have
+// ---- the ring of tile slots ---------------------------------------------------------------
+// Tile t uses slot t & slot_mask; its flag / look-back word carries the generation epoch + (t >> slot_shift), so a slot that
+// still holds an older tile reads as "not published" and the ring never has to be cleared (streams of any length).
+__device__ __forceinline__ TileSlot* slot_of(const Params& P, uint64_t t) { return &P.slots[t & P.slot_mask]; }
+__device__ __forceinline__ uint32_t epoch_of(const Params& P, uint32_t epoch, uint64_t t) { return (epoch + (uint32_t)(t >> P.slot_shift)) & 0x3FFFFFFFu; }
+
+// Exclusive prefix of tile t (general state: FASTA), computed by one whole warp: lane l inspects tile base-l, so 32
+// predecessors are examined per step (a serial walk makes look-backs slow, which lengthens the window of tiles that have
 // only published aggregates, which makes look-backs slower still).
-// BLOCKING = false: returns false (result undefined) instead of waiting when a needed predecessor has not
-// published yet, so that a producer warp can do other work and retry.
-template <bool BLOCKING = true>
-__device__ __forceinline__ bool warp_lookback_try(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, SState& out) {
+__device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
     SState suffix = identity_state();
     int64_t base = (int64_t)t - 1;
     uint32_t backoff = 32;                                          // ns; doubles up to 256 (polling costs issue slots and L2 traffic)
     for (;;) {
         const int64_t j = base - (int64_t)lane;
         uint32_t st = 2;                                            // before the first tile: inclusive(identity)
-        if (j >= 0) { const uint32_t f = ld_acquire_u32(&P.slots[j].flag); st = ((f >> 2) == epoch) ? (f & 3u) : 0u; }
+        if (j >= 0) { const uint32_t f = ld_acquire_u32(&slot_of(P, (uint64_t)j)->flag); st = ((f >> 2) == epoch_of(P, epoch, (uint64_t)j)) ? (f & 3u) : 0u; }
         const uint32_t inc_mask = __ballot_sync(0xffffffffu, st == 2), nr_mask = __ballot_sync(0xffffffffu, st == 0);
         const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
         const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if (nr_mask & need) { if (!BLOCKING) return false; __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
+        if (nr_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
         const int top = first_inc < 32 ? first_inc : 31;
         SState acc = identity_state();                              // lanes above `top` contribute the identity
-        if (j >= 0 && (int)lane <= top) acc = ((int)lane == first_inc) ? P.slots[j].inc : P.slots[j].agg;
+        if (j >= 0 && (int)lane <= top) acc = ((int)lane == first_inc) ? slot_of(P, (uint64_t)j)->inc : slot_of(P, (uint64_t)j)->agg;
         // ordered tree reduction: lane l holds tile base-l, higher lanes are EARLIER tiles; combine() is associative
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -756,21 +710,131 @@ __device__ __forceinline__ bool warp_lookback_try(const Params& P, uint64_t t, u
         }
         acc = shfl_state(acc, 0);
         suffix = combine(acc, suffix);
-        if (first_inc < 32) { out = suffix; return true; }
+        if (first_inc < 32) return suffix;
         base -= 32;
     }
 }
-__device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
-    SState r;
-    warp_lookback_try<true>(P, t, epoch, lane, r);
-    return r;
+
+// ---- FASTQ look-back on one 64-bit word per tile (round 2) ------------------------------------------------------
+// FASTQ line roles need the newline ordinal mod 4 only, and the end-of-stream rules (fastq.rs:337-356) only whether at least
+// four newlines exist: the prefix is the 3-bit monoid  enc(c) = (c & 3) | (c >= 4 ? 4 : 0),  enc(a + b) = sum of the low parts
+// mod 4, saturation bit = either saturated or the low parts reach 4.  A tile publishes ONE word, first with its own count
+// (state 1), later with the inclusive prefix (state 2):  generation (30 bits) << 34 | state << 32 | enc.  The word is its own
+// payload: a single relaxed load per predecessor, 128 predecessors per step (4 per lane, all loads in flight together), and
+// the fold is two warp reductions - instead of a 64-byte state per predecessor behind a flag and a shuffle tree of combines.
+// The r1 look-back of the headline run took 33 000 cycles per tile (NTG_STATS) and the tile loop ran 12 % faster without it.
+// The positions of the last four newlines before a tile (line lengths of the lines that cross into it) come from the
+// aggregates of its nearest predecessors (collect_last).
+constexpr int LBQ_G = 4;
+__host__ __device__ __forceinline__ uint32_t enc_count(uint64_t c) { return (uint32_t)(c & 3u) | (c >= 4 ? 4u : 0u); }
+__host__ __device__ __forceinline__ uint32_t enc_combine(uint32_t a, uint32_t b) {
+    const uint32_t s = (a & 3u) + (b & 3u);
+    return (s & 3u) | ((a | b) & 4u) | (s >= 4 ? 4u : 0u);
+}
+__device__ __forceinline__ unsigned long long cw_make(uint32_t gen, uint32_t state, uint32_t enc) {
+    return ((unsigned long long)gen << 34) | ((unsigned long long)state << 32) | enc;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// encoded exclusive prefix of tile t (t > 0); whole warp.  Ends with a fence: the aggregates of every predecessor are visible.
+__device__ __forceinline__ uint32_t fastq_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
+    uint32_t suffix = 0;
+    int64_t base = (int64_t)t - 1;                                  // nearest predecessor not folded yet
+    uint32_t backoff = 32;
+    for (;;) {
+        const int64_t j0 = base - (int64_t)lane * LBQ_G;            // this lane: tiles j0, j0-1, ... (nearest first)
+        unsigned long long w[LBQ_G];
+#pragma unroll
+        for (int g = 0; g < LBQ_G; g++) { const int64_t j = j0 - g; w[g] = j >= 0 ? ld_relaxed_u64(&P.cw[(uint64_t)j & P.slot_mask]) : 0ull; }
+        uint32_t lane_enc = 0, lane_state = 0;                      // 0: G aggregates folded, 1: reached an inclusive prefix, 2: blocked
+#pragma unroll
+        for (int g = 0; g < LBQ_G; g++) {
+            const int64_t j = j0 - g;
+            uint32_t st = 2, en = 0;                                 // before the first tile: inclusive(identity)
+            if (j >= 0) { st = ((uint32_t)(w[g] >> 34) == epoch_of(P, epoch, (uint64_t)j)) ? (uint32_t)(w[g] >> 32) & 3u : 0u; en = (uint32_t)w[g] & 7u; }
+            if (lane_state == 0) {
+                if (st == 0) lane_state = 2;
+                else { lane_enc = enc_combine(lane_enc, en); if (st == 2) lane_state = 1; }
+            }
+        }
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, lane_state == 1), blk_mask = __ballot_sync(0xffffffffu, lane_state == 2);
+        const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
+        const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
+        if (blk_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
+        const uint32_t mine = ((int)lane <= first_inc) ? lane_enc : 0u;
+        const uint32_t low = __reduce_add_sync(0xffffffffu, mine & 3u), sat = __reduce_or_sync(0xffffffffu, mine & 4u);
+        suffix = enc_combine((low & 3u) | sat | (low >= 4 ? 4u : 0u), suffix);
+        if (first_inc < 32) break;
+        base -= 32 * LBQ_G;
+    }
+    __threadfence();                                                // words observed -> aggregates (slot->agg) readable
+    return suffix;
+}
+// the four most recent newline positions before tile `t_excl` (newest first, NONE-padded) from the aggregates of the tiles
+// before it; every one of them has been published (fastq_lookback has seen their words).  One thread.
+constexpr int LAST_WALK_MAX = 4096;
+__device__ __forceinline__ void collect_last(const Params& P, uint64_t t_excl, uint64_t* last, uint32_t filled, uint32_t& slow) {
+    int64_t j = (int64_t)t_excl - 1;
+    for (int steps = 0; filled < 4 && j >= 0; j--, steps++) {
+        if (steps >= LAST_WALK_MAX) { slow |= FLAG_HALO_OVERFLOW; break; }     // a line spanning thousands of tiles: exact path
+        const SState* a = &slot_of(P, (uint64_t)j)->agg;
+        const uint64_t c = a->count;
+        for (uint32_t i = 0; i < 4 && i < c && filled < 4; i++) last[filled++] = a->last[i];
+    }
+    for (; filled < 4; filled++) last[filled] = NONE;
+}
+
+// Exclusive prefix of tile t in the form the line events need, by one whole warp (result in every lane).  FASTQ: `count` holds
+// enc(newlines before t) - its low two bits are the line phase - and last[] the last four newline positions; FASTA: the
+// general state.
+__device__ __forceinline__ SState tile_prefix(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, bool fasta, uint32_t& slow) {
+    SState pre = identity_state();
+    if (t == 0) return pre;
+    if (fasta) return warp_lookback(P, t, epoch, lane);
+    pre.count = fastq_lookback(P, t, epoch, lane);
+    if (lane == 0) collect_last(P, t, pre.last, 0, slow);
+#pragma unroll
+    for (int i = 0; i < 4; i++) pre.last[i] = __shfl_sync(0xffffffffu, pre.last[i], 0);
+    return pre;
+}
+// one thread: make the tile's aggregate visible to the look-backs of its successors
+__device__ __forceinline__ void publish_aggregate(const Params& P, uint64_t t, uint32_t epoch, const SState& agg, bool fasta) {
+    TileSlot* slot = slot_of(P, t);
+    slot->agg = agg;
+    if (fasta) { __threadfence(); st_release_u32(&slot->flag, epoch_of(P, epoch, t) * 4 + 1); }
+    else st_release_u64(&P.cw[t & P.slot_mask], cw_make(epoch_of(P, epoch, t), 1, enc_count(agg.count)));
+}
+// one thread: publish the inclusive prefix of tile t (and hand the stream's final state to k_finalize)
+__device__ __forceinline__ void publish_inclusive(const Params& P, uint64_t t, uint32_t epoch, const SState& pre, const SState& agg, bool fasta) {
+    SState inc;
+    if (fasta) {
+        TileSlot* slot = slot_of(P, t);
+        inc = combine(pre, agg);
+        slot->inc = inc;
+        __threadfence();
+        st_release_u32(&slot->flag, epoch_of(P, epoch, t) * 4 + 2);
+    } else {
+        inc = identity_state();
+        inc.count = enc_combine((uint32_t)pre.count, enc_count(agg.count));
+        st_release_u64(&P.cw[t & P.slot_mask], cw_make(epoch_of(P, epoch, t), 2, (uint32_t)inc.count));
+        if (t + 1 == P.num_tiles) {                                // newest four newline positions of the whole stream
+            int f = 0;
+            for (int i = 0; i < 4 && (uint64_t)i < agg.count; i++) inc.last[f++] = agg.last[i];
+            for (int i = 0; i < 4 && f < 4; i++) inc.last[f++] = pre.last[i];
+        }
+    }
+    if (t + 1 == P.num_tiles) *P.final_state = inc;
 }
 
 // =============================================================================== the kernel
 __device__ __forceinline__ uint8_t byte_at(const Params& P, const uint8_t* sb, uint64_t tile_start, uint32_t halo, uint64_t gpos) {
     // global position -> byte, from shared memory when resident, else from global memory
     if (gpos + halo >= tile_start && gpos < tile_start + P.tile_bytes) return sb[(int64_t)gpos - (int64_t)tile_start];
-    return gpos < P.n ? P.bytes[gpos] : 0;
+    return (gpos < P.n && gpos >= P.gmin) ? P.bytes[gpos] : 0;
 }
 __device__ __forceinline__ uint8_t class_of(int i) {
     uint8_t c = c_ncls[i];
@@ -796,14 +860,17 @@ __device__ __noinline__ bool walk_fast_cold(const uint8_t* sb, const uint8_t* lu
 // every warp would otherwise walk each item twice; a clean item puts the lane back.
 template <int KW, bool MINI, int W, int FK, int FM>
 __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, const uint32_t* comb, int a, int b, int lo,
-                                         bool lo_exact, const Params& P, Acc& acc, bool fasta, uint32_t& slow, uint32_t& mode, uint32_t one) {
+                                         bool lo_exact, const Params& P, Acc& acc, bool fasta, uint32_t& slow, uint32_t& mode) {
     if (b > a && sb[b - 1] == '\r') b--;                   // a trailing '\r' is deleted by normalize: nothing to walk
     if (b <= a) return;
     constexpr bool ONE = FK >= 21 && FK <= 31;              // constant-folded one-word shapes (clean / fast walkers)
     int got = 0; uint64_t wcodes = 0;
     const int ws = ONE ? find_ws_codes(sb, lut, a, lo, lo_exact, (int)P.k, slow, got, wcodes) : find_ws(sb, lut, a, lo, lo_exact, (int)P.k, slow);
     if (FK > 32) {
-        if (!__any_sync(__activemask(), mode != 0u) && walk_clean2<(FK > 32 ? FK : 51)>(sb, comb, ws, b, acc)) return;
+        if (!__any_sync(__activemask(), mode != 0u) && walk_clean2<(FK > 32 ? FK : 51)>(sb, comb, ws, b, acc)) {
+            if (fasta) acc.n_bases += (uint64_t)(b - a);   // no deleted bytes in [ws,b): every byte of the item is a base
+            return;
+        }
         mode = 1u;                                             // an item the clean walker refused: the warp's next item goes straight
         uint32_t any_bad = 0;                                  // to the generic walker, and comes back once an item was all ACGT
         for (int q = ws; q < b; q++) any_bad |= lut[sb[q]];
@@ -814,8 +881,8 @@ __device__ __forceinline__ void run_item(const uint8_t* sb, const uint8_t* lut, 
         bool done = false;
         if (!__any_sync(__activemask(), mode != 0u)) {
             // a warm-up that crosses deleted bytes (wrapped FASTA: the previous line break) is fed from the register
-            if (got == CK - 1 && a - ws != got) done = walk_clean<CK, CM, true>(sb, comb, a, b, wcodes, one, acc);
-            else done = walk_clean<CK, CM, false>(sb, comb, ws, b, 0, one, acc);
+            if (got == CK - 1 && a - ws != got) done = walk_clean<CK, CM, true>(sb, comb, a, b, wcodes, acc);
+            else done = walk_clean<CK, CM, false>(sb, comb, ws, b, 0, acc);
         }
         if (!done) {
             uint32_t seen = 0x80u;
@@ -867,6 +934,9 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
 }
 
 
+#ifndef NTG_EARLY_TICKET
+#define NTG_EARLY_TICKET 0                           // 1: the coordinator claims the CTA's next tile right after publishing this one's aggregate and
+#endif                                               //    prefetches it into L2; 0: walker thread 0 claims it at the end of its walk (no prefetch)
 #ifndef NTG_STATS
 #define NTG_STATS 0                                  // 1: per-CTA cycle accounting into tallies[9..15] (ntg_tallies.reserved[2..6]):
 #endif                                               //    [9] sum of CTA lifetimes, [10] coordinator cycles inside look-backs, [11] look-backs,
@@ -923,21 +993,8 @@ __host__ __device__ __forceinline__ void first_lines_event(const uint8_t* __rest
 __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t epoch, uint32_t lane, Acc& acc, uint32_t& slow) {
     const uint64_t t = S.pend_t;
     const SState agg = S.pend_agg;
-    SState pre = identity_state();
-#ifdef NTG_EXP_NOLB                                  // TIMING EXPERIMENT ONLY (wrong results): what the look-back costs the tile loop
-    pre.count = S.pend_guess;
-    if (t + 1 == P.num_tiles && lane == 0) { SState inc = combine(pre, agg); inc.count = 4 * (P.n / 316); *P.final_state = inc; }
-#else
-    if (t > 0) pre = warp_lookback(P, t, epoch, lane);
-    if (lane == 0) {
-        const SState inc = combine(pre, agg);
-        TileSlot* slot = &P.slots[t];
-        slot->inc = inc;
-        __threadfence();
-        st_release_u32(&slot->flag, epoch * 4 + 2);
-        if (t + 1 == P.num_tiles) *P.final_state = inc;
-    }
-#endif
+    const SState pre = tile_prefix(P, t, epoch, lane, false, slow);      // (only FASTQ tiles are deferred)
+    if (lane == 0) publish_inclusive(P, t, epoch, pre, agg, false);
     const uint32_t ord0 = (uint32_t)(pre.count & 3);
     if (S.pend_guess != ord0) slow |= FLAG_SPEC_MISS;
     const uint32_t Cs = S.pend_cs;
@@ -983,12 +1040,11 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 
     // Tiles are handed out by an atomic ticket (round 2, measured: C2 +2 %, C3 +57 % over static round-robin: with aggregates
     // published early and the look-back deferred a late claimer no longer stalls its successors, and SMs that run ahead take
-    // more tiles instead of polling for slower predecessors).  Walker thread 0 claims the NEXT ticket when its own walk is
-    // done, so the atomic's latency hides behind the end-of-tile barrier.
-    if (tid == 0) { S.tile_idx_next = atomicAdd(ticket, 1u); S.one_word = P.one; }
+    // more tiles instead of polling for slower predecessors).  The coordinator claims the CTA's NEXT ticket as soon as it has
+    // published this tile's aggregate and prefetches that tile into L2 (NTG_EARLY_TICKET).
+    if (tid == 0) S.tile_idx_next = atomicAdd(ticket, 1u);
     __syncthreads();
     uint32_t next_ticket = S.tile_idx_next;
-    const uint32_t one_r = *reinterpret_cast<volatile uint32_t*>(&S.one_word);
     for (;;) {
         const uint64_t t = tile_begin + (uint64_t)next_ticket;
         if (t >= tile_end) break;
@@ -1025,7 +1081,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         // even for a tile made of newlines (a run of blank lines is valid FASTA / FASTQ tail).
         static_assert(MAXROUNDS == 2 && NTW * ROWB < (1 << 17) && (TILE / ROWB - NTW) * ROWB < (1 << 15), "packed scan: 17 + 15 bits");
         uint32_t Cpacked;
-        const uint32_t offp = block_excl_scan(cnt[0] | (cnt[1] << 17), &Cpacked, S.warp_tmp);
+        const uint32_t offp = block_excl_scan(cnt[0] | (cnt[1] << 17), &Cpacked, S.warp_tmp[0]);
         const uint32_t C0 = Cpacked & 0x1FFFFu, C = C0 + (Cpacked >> 17);
         const bool overflow = C > NLMAX;
         if (overflow) slow |= FLAG_NL_OVERFLOW;
@@ -1065,8 +1121,8 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         }
         uint32_t last_start1 = 0, nstarts_tot = 0;
         if (fasta) {
-            last_start1 = block_incl_max(my_last_start, S.warp_tmp);
-            uint32_t tot; block_excl_scan(my_nstarts, &tot, S.warp_tmp); nstarts_tot = tot;
+            last_start1 = block_incl_max(my_last_start, S.warp_tmp[1]);
+            uint32_t tot; block_excl_scan(my_nstarts, &tot, S.warp_tmp[2]); nstarts_tot = tot;
             if (tid == NWK - 1) S.bcast[0] = (int32_t)last_start1;
             tile_sync();
             last_start1 = (uint32_t)S.bcast[0];
@@ -1090,11 +1146,19 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 agg.first_nl = Cs ? tile_start + S.nl[0] : NONE;
                 if (last_start1) { const uint32_t Lh = last_start1 - 1; agg.hdr = (Lh < Cs) ? tile_start + S.nl[Lh] : INHDR; }
             }
-            TileSlot* slot = &P.slots[t];
-            if (t > 0 && lane == 0) {
-                slot->agg = agg;
-                __threadfence();
-                st_release_u32(&slot->flag, epoch * 4 + 1);
+            if (lane == 0) {
+                publish_aggregate(P, t, epoch, agg, fasta);
+#if NTG_EARLY_TICKET
+                // the next tile of this CTA: claimed now so that it can be pulled into L2 while the walkers work on this one
+                const uint32_t nx = atomicAdd(ticket, 1u);
+                S.tile_idx_next = nx;
+                const uint64_t tn = tile_begin + (uint64_t)nx;
+                if (tn < tile_end) {
+                    const uint64_t ns = tn * (uint64_t)TB;
+                    const uint32_t nbytes = (uint32_t)min((uint64_t)TB, P.n - ns) & ~15u;
+                    if (nbytes) bulk_prefetch_l2(P.bytes + ns, nbytes);
+                }
+#endif
             }
             __syncwarp();
 #if NTG_STATS
@@ -1114,14 +1178,10 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                     S.pend_valid = 1;
                 }
             } else {
-                if (t > 0) pre = warp_lookback(P, t, epoch, lane);
+                pre = tile_prefix(P, t, epoch, lane, fasta, slow);
                 if (lane == 0) {
-                    const SState inc = combine(pre, agg);
-                    slot->inc = inc;
-                    __threadfence();
-                    st_release_u32(&slot->flag, epoch * 4 + 2);
+                    publish_inclusive(P, t, epoch, pre, agg, fasta);
                     S.prefix = pre;
-                    if (t + 1 == P.num_tiles) *P.final_state = inc;
                     __threadfence_block();
                     S.prefix_seq = my_seq + 1;
                 }
@@ -1225,7 +1285,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                     if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                     int lo; bool lo_exact;
                     fastq_bound(i, a, lo, lo_exact);
-                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, false, slow, mode, one_r);
+                    run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, false, slow, mode);
                 }
             }
         } else {
@@ -1241,7 +1301,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             const uint32_t i0 = min(tid * per, Cs + 1), i1 = min(i0 + per, Cs + 1);
             uint32_t lm = 0;
             for (uint32_t i = i0; i < i1; i++) if (i < Cs && is_header(i)) lm = max(lm, (uint32_t)S.nl[i] + 1 + HALO);
-            const uint32_t incl = block_incl_max(lm, S.warp_tmp);
+            const uint32_t incl = block_incl_max(lm, S.warp_tmp[3]);
             uint32_t run = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) run = 0;
             __shared__ uint32_t s_prev[NT / 32 + 1];
@@ -1260,13 +1320,15 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 if (b - a > SEG) { const uint32_t li = atomicAdd(&S.n_long, 1u); if (li < LONGMAX) S.long_line[li] = i; continue; }
                 int lo; bool lo_exact;
                 fasta_bound(i, a, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, true, slow, mode, one_r);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, true, slow, mode);
             }
         }
 #if NTG_STATS
         const long long st_done = clock64();
 #endif
+#if !NTG_EARLY_TICKET
         if (tid == 0) S.tile_idx_next = atomicAdd(ticket, 1u);      // the next tile of this CTA (read after the barrier)
+#endif
         tile_sync();
         next_ticket = S.tile_idx_next;
 #if NTG_STATS
@@ -1296,7 +1358,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 const int a = la + (int)(pc - S.long_pref[j]) * PSEG, b = min(a + PSEG, lb);
                 int lo; bool lo_exact;
                 if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
-                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode, one_r);
+                run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode);
             }
             tile_sync();                               // (no long lines: nothing read the tile since the barrier above, and
         }                                                  //  the reset of S.n_long at the next tile stores the value it holds)

@@ -10,9 +10,11 @@ struct FusedControl {           // device-resident control block, zeroed per cal
 };
 static_assert(sizeof(FusedControl) == 128 + 4 + 59 * 4, "layout");
 constexpr int FUSED_MAX_LAUNCHES = 59;
+constexpr uint32_t SLOT_SHIFT = 16;      // 65 536 slots (16 MiB) + 65 536 words: far more than the tiles in flight plus the look-back reach
 
 struct FusedState {
-    fused::TileSlot* slots = nullptr; uint64_t slots_cap = 0;
+    fused::TileSlot* slots = nullptr;        // ring of 1 << SLOT_SHIFT tile slots + look-back words (never cleared: generations)
+    unsigned long long* cw = nullptr;
     FusedControl* ctrl = nullptr;
     fused::SState* final_state = nullptr;
     FusedControl* h_ctrl = nullptr;          // pinned
@@ -58,6 +60,10 @@ static int fused_init(ntg_ctx* ctx) {
     ctx->fused = st;
     NTG_CUDA(ctx, cudaMalloc((void**)&st->ctrl, sizeof(FusedControl)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->final_state, sizeof(fused::SState)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->slots, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->cw, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long)));
+    NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot), ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(st->cw, 0, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long), ctx->stream));
     NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_ctrl, sizeof(FusedControl)));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k0));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k1));
@@ -81,7 +87,7 @@ static int fused_init(ntg_ctx* ctx) {
 static void fused_destroy(ntg_ctx* ctx) {
     FusedState* st = ctx->fused;
     if (!st) return;
-    cudaFree(st->slots); cudaFree(st->ctrl); cudaFree(st->final_state); cudaFreeHost(st->h_ctrl); cudaFree(st->feed_buf);
+    cudaFree(st->slots); cudaFree(st->cw); cudaFree(st->ctrl); cudaFree(st->final_state); cudaFreeHost(st->h_ctrl); cudaFree(st->feed_buf);
     if (st->ev_k0) cudaEventDestroy(st->ev_k0);
     if (st->ev_k1) cudaEventDestroy(st->ev_k1);
     if (st->ev_ready) cudaEventDestroy(st->ev_ready);
@@ -130,16 +136,16 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
     st->general_tile_bytes = tile_bytes;
     if ((reinterpret_cast<uintptr_t>(dbytes) & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
-    if (num_tiles > st->slots_cap) {
-        cudaFree(st->slots); st->slots = nullptr; st->slots_cap = 0;
-        NTG_CUDA(ctx, cudaMalloc((void**)&st->slots, num_tiles * sizeof(fused::TileSlot)));
-        NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, num_tiles * sizeof(fused::TileSlot), ctx->stream));
-        st->slots_cap = num_tiles; st->epoch = 0;
+    // a fresh range of slot generations for this call: the previous call used epoch .. epoch + (its tiles >> SLOT_SHIFT)
+    st->epoch = (st->epoch + 1 + (uint32_t)(st->P.num_tiles >> SLOT_SHIFT)) & 0x3FFFFFFFu;
+    if (st->epoch + (num_tiles >> SLOT_SHIFT) + 2 >= 0x3FFFFFFFull) {       // (once per 2^30 calls) start the generations over
+        NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot), ctx->stream));
+        NTG_CUDA(ctx, cudaMemsetAsync(st->cw, 0, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long), ctx->stream));
+        st->epoch = 1;
     }
-    st->epoch++;
     NTG_CUDA(ctx, cudaMemsetAsync(st->ctrl, 0, sizeof(FusedControl), ctx->stream));
     fused::Params& P = st->P;
-    P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.ticket = nullptr;
+    P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.cw = st->cw; P.slot_mask = (1u << SLOT_SHIFT) - 1; P.slot_shift = SLOT_SHIFT; P.gmin = 0; P.ticket = nullptr;
     P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
     P.spec = (allow_spec && format == NTG_FMT_FASTQ && !(cfg->flags & NTG_TALLY_NO_SPECULATION)) ? 1 : 0;

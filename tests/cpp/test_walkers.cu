@@ -48,7 +48,7 @@ static bool item(const uint8_t* sb, const Luts& L, int a, int b, int lo, int whi
     if (b <= a) return true;
     uint32_t slow = 0;
     const int ws = fused::find_ws(sb, g_cls, a, lo, true, K, slow);
-    if ((which & CLEAN) && fused::walk_clean<K, M, false>(sb, L.comb, ws, b, 0, 1u, acc)) { if (used) *used = CLEAN; return true; }
+    if ((which & CLEAN) && fused::walk_clean<K, M, false>(sb, L.comb, ws, b, 0, acc)) { if (used) *used = CLEAN; return true; }
     fused::FastLuts FL{g_cls, L.rins, L.comb};
     if ((which & FAST) && fused::walk_fast<K, M>(sb, FL, ws, b, acc)) { if (used) *used = FAST; return true; }
     if (which & GENERIC) {
@@ -286,7 +286,7 @@ static int run_wrapped(std::mt19937_64& rng, int iters, const char* name) {
             if (b <= a) continue;
             uint32_t slow = 0; int got = 0; uint64_t wcodes = 0;
             const int ws = fused::find_ws_codes(sb, g_cls, a, 0, true, K, slow, got, wcodes);
-            if (got == K - 1 && a - ws != got && fused::walk_clean<K, M, true>(sb, L.comb, a, b, wcodes, 1u, acc)) { n_w++; continue; }
+            if (got == K - 1 && a - ws != got && fused::walk_clean<K, M, true>(sb, L.comb, a, b, wcodes, acc)) { n_w++; continue; }
             n_other++;
             item<K, M>(sb, L, a, b, 0, CLEAN | FAST | GENERIC, acc);
         }
