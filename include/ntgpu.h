@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NTG_ABI_VERSION 2
+#define NTG_ABI_VERSION 3
 
 typedef enum ntg_status {
     NTG_OK = 0,
@@ -116,8 +116,18 @@ typedef struct ntg_records {
     void* _priv;
 } ntg_records;
 
-int ntg_parse_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, ntg_records** out);
+int ntg_parse_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, ntg_records** out);      /* n < 4 GiB: one window */
 void ntg_records_free(ntg_records* r);
+/* The incremental form behind `FastxReader::next()` over an `R: Read` of any length (src/parser/mod.rs:85-87, refill loop
+ * src/parser/fastq.rs:312-384, src/parser/fasta.rs:291-346): one WINDOW of the stream per call (n < 4 GiB).
+ *   format  : NTG_FMT_NONE on the first window (sniff), afterwards the format the first window reported
+ *   at_eof  : 0 = the stream continues behind this window: only records complete inside it are delivered (FASTQ: four
+ *             newlines; FASTA: followed by another '>' line start) and no end-of-stream rule runs; 1 = last window
+ *   consumed: offset of the first byte not covered by a delivered record — the next window starts there (0 with no
+ *             error: not even one complete record, pass a larger window)
+ * Offsets, lines and record indices in *out are relative to the window; out->final_line is the (relative, 1-based) line at
+ * `consumed`, so the caller carries  line_base += final_line - 1,  record_base += n_records,  byte_base += consumed. */
+int ntg_parse_fastx_chunk(ntg_ctx* ctx, const uint8_t* bytes, size_t n, int format, int at_eof, ntg_records** out, uint64_t* consumed);
 
 /* ---- (2) Sequence trait, batch form -----------------------------------------------------
  * Every call works on a batch of sequences so that one FFI crossing amortises over many
@@ -188,6 +198,13 @@ typedef struct ntg_tally_config {
 } ntg_tally_config;
 /* diagnostic: FASTQ tiles wait for the look-back instead of starting on the locally inferred line phase (same results) */
 #define NTG_TALLY_NO_SPECULATION 1u
+/* enqueue/collect form only, after ntg_comm_init: the tallies of all ranks are summed by ONE ncclAllReduce enqueued on the
+ * compute stream right behind the kernel (k_finalize writes the NCCL send buffer; no host round trip in between).  collect
+ * then returns the job-wide tallies on every rank.  If any rank's shard needed the host (parse error replay, exact path)
+ * collect returns that rank's LOCAL tallies with NTG_RESERVED_NOT_REDUCED set in reserved[0]: reduce them with
+ * ntg_comm_allreduce_tallies. */
+#define NTG_TALLY_ALLREDUCE 2u
+#define NTG_RESERVED_NOT_REDUCED (1ull << 32)
 
 typedef struct ntg_tallies {
     uint64_t n_records;
@@ -204,7 +221,8 @@ typedef struct ntg_tallies {
                                   reserved[1]: non-zero when a speculated FASTQ line phase was wrong and the call re-ran without speculation */
 } ntg_tallies;
 
-/* host bytes: H2D copies are pipelined with the kernel inside the call (the end-to-end path) */
+/* host bytes of ANY size: streamed through three 64 MiB device segments, H2D copies overlapped with the kernel of the
+ * previous segment (the end-to-end path; pinned caller memory copies at PCIe speed).  Device memory use is bounded. */
 int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tally_config* cfg,
                     ntg_tallies* out, ntg_parse_error* err);
 /* bytes already resident in HBM (dptr 16-byte aligned) */
@@ -214,6 +232,32 @@ int ntg_tally_fastx_device(ntg_ctx* ctx, uint64_t dptr, size_t n, const ntg_tall
  * `fused_kernel_ms` (may be NULL) receives the CUDA-event duration of the fused kernel alone. */
 int ntg_tally_fastx_device_enqueue(ntg_ctx* ctx, uint64_t dptr, size_t n, const ntg_tally_config* cfg);
 int ntg_tally_fastx_device_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, float* fused_kernel_ms);
+
+/* ---- (3b) streaming session: the tally path over an `R: Read` ---------------------------------
+ * replaces: parse_fastx_reader<R: Read + Send>(reader) (src/parser/mod.rs:85-150) + the per-record loop, for streams of
+ * unknown length (stdin, sockets, decompressors).  Pieces of any size are staged in pinned host buffers and go to the device
+ * as 64 MiB segments while the next one fills; the look-back state carries across kernel launches.  Iterator semantics are
+ * kept without re-reading the stream: a parse error ends the stream in front of the failing record (the launch that met it is
+ * replayed truncated while its segment is still resident) and is reported by finish with the reference's kind / line / id.
+ * Inputs that need the exact record-table path (newline-dense tiles, whitespace runs > 128 B inside sequences, records
+ * longer than a segment that fail) make finish return NTG_EUNSUPPORTED: use ntg_tally_fastx on the whole input.
+ * One session per context at a time; not thread-safe (the `&mut self` contract of FastxReader, parser/utils.rs:119-130). */
+typedef struct ntg_stream ntg_stream;
+int ntg_stream_open(ntg_ctx* ctx, const ntg_tally_config* cfg, ntg_stream** out);
+int ntg_stream_feed(ntg_stream* s, const uint8_t* bytes, size_t n);          /* copies into the staging buffer */
+/* zero-copy producers (read(2), inflate): write up to *avail bytes at *ptr (pinned), then commit what was written */
+int ntg_stream_acquire(ntg_stream* s, uint8_t** ptr, size_t* avail);
+int ntg_stream_commit(ntg_stream* s, size_t n);
+/* one more piece of a gzip stream (magic 1f 8b; src/parser/mod.rs:96-108): multi-member like flate2::MultiGzDecoder.
+ * threads > 1 and a BGZF file (member sizes in the gzip extra field): members are inflated in parallel, in place. */
+int ntg_stream_feed_gz(ntg_stream* s, const uint8_t* gz, size_t n, int threads);
+int ntg_stream_finish(ntg_stream* s, ntg_tallies* out, ntg_parse_error* err);
+uint64_t ntg_stream_bytes(const ntg_stream* s);                              /* decompressed bytes fed so far */
+void ntg_stream_close(ntg_stream* s);
+/* parse_fastx_file(path) (src/parser/mod.rs:160-165) for the tally path: reads the file piecewise into the staging buffers,
+ * inflating gzip on the way (`threads` workers for BGZF).  bzip2 / xz / zstd files: NTG_EUNSUPPORTED (zlib only). */
+int ntg_tally_fastx_file(ntg_ctx* ctx, const char* path, const ntg_tally_config* cfg, int threads,
+                         ntg_tallies* out, ntg_parse_error* err);
 
 /* ---- (4) synthetic inputs (DESIGN.md "Synthetic inputs"; same bytes as oracle/synth.hpp) ---- */
 int ntg_synth_fastq_device(ntg_ctx* ctx, uint64_t dptr, uint64_t seed, uint64_t rec0, uint64_t nrec,

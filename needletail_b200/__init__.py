@@ -108,6 +108,16 @@ def load_library():
         "ntg_event_elapsed_ms": ([vp, C.c_int, C.c_int, P(C.c_float)], C.c_int),
         "ntg_parse_fastx": ([vp, vp, sz, P(P(_Records))], C.c_int),
         "ntg_records_free": ([P(_Records)], None),
+        "ntg_parse_fastx_chunk": ([vp, vp, sz, C.c_int, C.c_int, P(P(_Records)), P(u64)], C.c_int),
+        "ntg_stream_open": ([vp, P(_TallyConfig), P(vp)], C.c_int),
+        "ntg_stream_feed": ([vp, vp, sz], C.c_int),
+        "ntg_stream_acquire": ([vp, P(vp), P(sz)], C.c_int),
+        "ntg_stream_commit": ([vp, sz], C.c_int),
+        "ntg_stream_feed_gz": ([vp, vp, sz, C.c_int], C.c_int),
+        "ntg_stream_finish": ([vp, P(_Tallies), P(_ParseError)], C.c_int),
+        "ntg_stream_bytes": ([vp], u64),
+        "ntg_stream_close": ([vp], None),
+        "ntg_tally_fastx_file": ([vp, cp, P(_TallyConfig), C.c_int, P(_Tallies), P(_ParseError)], C.c_int),
         "ntg_normalize": ([vp, vp, vp, sz, C.c_int, vp, vp, vp], C.c_int),
         "ntg_strip_returns": ([vp, vp, vp, sz, vp, vp, vp], C.c_int),
         "ntg_reverse_complement": ([vp, vp, vp, sz, vp], C.c_int),
@@ -249,6 +259,45 @@ class Context:
         finally:
             self.lib.ntg_records_free(out)
 
+    def parse_chunks(self, data, window=1 << 30):
+        """Generator of Parsed, one per window of `window` bytes (< 4 GiB) — ntg_parse_fastx_chunk: the incremental reader behind
+        FastxReader for inputs of any size.  Offsets, lines and error positions are made absolute; the last Parsed carries
+        the end-of-stream error, if any."""
+        arr = _as_u8(data)
+        n, pos, fmt, line_base, rec_base = arr.size, 0, 0, 0, 0
+        while True:
+            ln = min(window, n - pos)
+            at_eof = pos + ln == n
+            out = C.POINTER(_Records)(); consumed = C.c_uint64()
+            win = arr[pos:pos + ln]
+            self._ck(self.lib.ntg_parse_fastx_chunk(self.h, _ptr(win), ln, fmt, int(at_eof), C.byref(out), C.byref(consumed)))
+            try:
+                p = Parsed(win, out.contents)
+            finally:
+                self.lib.ntg_records_free(out)
+            fmt = {"fasta": 1, "fastq": 2}.get(p.format, 0)
+            if len(p.table):
+                p.table[:, [0, 1, 2, 3, 4, 7]] += np.uint64(pos)
+                if p.format == "fastq":
+                    p.table[:, [5, 6]] += np.uint64(pos)
+                p.table[:, 9] += np.uint64(line_base)
+                for r in p.records:
+                    r.byte += pos; r.line += line_base
+            p.err_line += line_base; p.err_record_index += rec_base
+            p.final_byte += pos; p.final_line += line_base
+            done = at_eof or p.err_kind is not None
+            if not done and consumed.value == 0:
+                if window >= 0xF0000000:
+                    raise NtgError(20, "a record larger than 3.75 GiB")
+                window = min(window * 2, 0xF0000000)
+                continue
+            yield p
+            if done:
+                return
+            line_base = p.final_line - 1
+            rec_base += len(p.table)
+            pos += consumed.value
+
     # ---- (2) Sequence trait, batch form
     def normalize(self, seqs, iupac=False):
         """list[bytes] -> (list[bytes], changed flags) — sequence::normalize per sequence"""
@@ -335,7 +384,7 @@ class Context:
         d = {f: int(getattr(t, f)) for f in TALLY_FIELDS}
         d["err_kind"] = ERROR_KINDS.get(e.kind) if e.kind else None
         d["err_line"] = int(e.line)
-        d["fallback"] = int(t.reserved[0])      # 0: the single-pass fused kernel produced the tallies
+        d["fallback"] = int(t.reserved[0]) & 0xFFFFFFFF      # 0: the single-pass fused kernel produced the tallies
         d["ws_handover"] = int(t.reserved[1])   # != 0: the warp-specialised kernel handed over to the general fused kernel
         d["ws_cycles"] = {"claim": int(t.reserved[2]), "scan": int(t.reserved[3]), "lookback_retry": int(t.reserved[4]),
                           "walker_wait": int(t.reserved[5]), "walker_work": int(t.reserved[6])}
@@ -358,15 +407,29 @@ class Context:
         self._ck(self.lib.ntg_tally_fastx_device(self.h, dptr, nbytes, C.byref(cfg), C.byref(t), C.byref(e)))
         return self._tally_result(t, e)
 
-    def tally_device_enqueue(self, dptr, nbytes, k, m=0, iupac=False, query=None):
+    def tally_device_enqueue(self, dptr, nbytes, k, m=0, iupac=False, query=None, allreduce=False):
+        """allreduce=True (after comm_init): the tallies of all ranks are summed by one in-stream ncclAllReduce (NTG_TALLY_ALLREDUCE)"""
         cfg = self._cfg(k, m, iupac, query)
+        if allreduce:
+            cfg.flags |= 2
         self._ck(self.lib.ntg_tally_fastx_device_enqueue(self.h, dptr, nbytes, C.byref(cfg)))
+
+    def tally_file(self, path, k, m=0, iupac=False, query=None, threads=1):
+        """parse_fastx_file for the tally path: plain or gzip (BGZF inflates on `threads` workers) — ntg_tally_fastx_file"""
+        cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
+        self._ck(self.lib.ntg_tally_fastx_file(self.h, os.fsencode(path), C.byref(cfg), threads, C.byref(t), C.byref(e)))
+        return self._tally_result(t, e)
+
+    def stream(self, k, m=0, iupac=False, query=None):
+        """A tally session over a stream of unknown length (parse_fastx_reader<R: Read>) — ntg_stream_*"""
+        return TallyStream(self, self._cfg(k, m, iupac, query))
 
     def tally_device_collect(self):
         t = _Tallies(); e = _ParseError(); ms = C.c_float()
         self._ck(self.lib.ntg_tally_fastx_device_collect(self.h, C.byref(t), C.byref(e), C.byref(ms)))
         d = self._tally_result(t, e)
         d["fused_kernel_ms"] = ms.value
+        d["not_reduced"] = bool(int(t.reserved[0]) >> 32)
         return d
 
     # ---- (4) synthetic inputs
@@ -394,6 +457,50 @@ class Context:
             setattr(t, f, d[f])
         self._ck(self.lib.ntg_comm_allreduce_tallies(self.h, C.byref(t)))
         return {f: int(getattr(t, f)) for f in TALLY_FIELDS}
+
+
+class TallyStream:
+    """ntg_stream: feed(bytes) / feed_gz(bytes, threads) any number of times, then finish() -> tallies dict."""
+
+    def __init__(self, ctx, cfg):
+        self.ctx, self.h = ctx, C.c_void_p()
+        ctx._ck(ctx.lib.ntg_stream_open(ctx.h, C.byref(cfg), C.byref(self.h)))
+
+    def feed(self, data):
+        arr = _as_u8(data)
+        self.ctx._ck(self.ctx.lib.ntg_stream_feed(self.h, _ptr(arr), arr.size))
+
+    def feed_ptr(self, host_ptr, nbytes):
+        self.ctx._ck(self.ctx.lib.ntg_stream_feed(self.h, host_ptr, nbytes))
+
+    def feed_gz(self, data, threads=1):
+        arr = _as_u8(data)
+        self.ctx._ck(self.ctx.lib.ntg_stream_feed_gz(self.h, _ptr(arr), arr.size, threads))
+
+    def feed_gz_ptr(self, host_ptr, nbytes, threads=1):
+        self.ctx._ck(self.ctx.lib.ntg_stream_feed_gz(self.h, host_ptr, nbytes, threads))
+
+    def bytes_fed(self):
+        return int(self.ctx.lib.ntg_stream_bytes(self.h))
+
+    def finish(self):
+        t = _Tallies(); e = _ParseError()
+        try:
+            self.ctx._ck(self.ctx.lib.ntg_stream_finish(self.h, C.byref(t), C.byref(e)))
+        finally:
+            self.close()
+        return self.ctx._tally_result(t, e)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ntg_stream_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def _snippet(seq, max_len=20):
@@ -533,14 +640,18 @@ def _decompress(raw):
 
 class FastxReader:
     """Iterator over records (python.rs:62-86); raises NeedletailError at the first invalid record,
-    after yielding the valid ones before it — the reference's iteration order."""
+    after yielding the valid ones before it — the reference's iteration order.  The input is scanned window by window
+    (Context.parse_chunks), so its size is not limited by the 32-bit offsets of one scanner call."""
+
+    WINDOW = 1 << 30
 
     def __init__(self, data, ctx=None):
         ctx = ctx or default_context()
         raw = _decompress(bytes(data))
         if len(data) >= 2 and len(raw) < 1 and raw != data:
             raise NeedletailError("EmptyFile")
-        self._p = ctx.parse(raw)
+        self._chunks = ctx.parse_chunks(raw, self.WINDOW)
+        self._p = next(self._chunks)
         if self._p.err_kind in ("EmptyFile", "UnknownFormat") and not self._p.records:
             raise self._p.error()          # parse_fastx_reader fails up front (mod.rs:88-91,44)
         self._i = 0
@@ -549,14 +660,18 @@ class FastxReader:
         return self
 
     def __next__(self):
-        if self._i < len(self._p.records):
-            r = self._p.records[self._i]
-            self._i += 1
-            return r
-        if self._p.err_kind and self._i == len(self._p.records):
-            self._i += 1
-            raise self._p.error()
-        raise StopIteration
+        while True:
+            if self._i < len(self._p.records):
+                r = self._p.records[self._i]
+                self._i += 1
+                return r
+            if self._p.err_kind and self._i == len(self._p.records):
+                self._i += 1
+                raise self._p.error()
+            nxt = next(self._chunks, None) if not self._p.err_kind else None
+            if nxt is None:
+                raise StopIteration
+            self._p, self._i = nxt, 0
 
 
 def parse_fastx_file(path, ctx=None):

@@ -10,7 +10,7 @@ SRC = os.path.join(HERE, "csrc", "ntgpu.cu")
 OUT = os.path.join(HERE, "libntgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-ldl"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-ldl", "-lz"]
 
 
 def sources():

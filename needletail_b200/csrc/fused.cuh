@@ -26,21 +26,35 @@
 #include "common.cuh"
 
 namespace fused {
-constexpr int NTW = 288;                 // 9 walker warps ...
-constexpr int NT = NTW + 32;             // ... + 1 coordinator warp (highest warp id); 2 CTAs per SM, 96 registers per thread
+// CTA shape (compile-time; tools/ab_shapes.sh measures the alternatives): walker threads, CTAs per SM, tile capacity, newline capacity
+#ifndef NTG_NTW
+#define NTG_NTW 288
+#endif
+#ifndef NTG_CTAS
+#define NTG_CTAS 2
+#endif
+#ifndef NTG_TILE_KB
+#define NTG_TILE_KB 84
+#endif
+#ifndef NTG_NLMAX
+#define NTG_NLMAX 2048
+#endif
+constexpr int NTW = NTG_NTW;             // walker warps x 32 ...
+constexpr int NT = NTW + 32;             // ... + 1 coordinator warp (highest warp id); NTG_CTAS CTAs per SM, 96 registers per thread
+constexpr int CTAS_PER_SM = NTG_CTAS;
 constexpr int ROWB = 256;                // P1 scans the tile in 256 B rows, one row per thread per round
 constexpr int ROWW = ROWB / 4;
-constexpr int TILE = 84 * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
+constexpr int TILE = NTG_TILE_KB * 1024;          // capacity of the shared-memory tile; the tile size in use is Params::tile_bytes
 constexpr int MAXROUNDS = (TILE / ROWB + NTW - 1) / NTW;   // 2  (rows are scanned by the walker threads)
 constexpr int HALO = 128;                // back halo (>= k-1 bases for k <= 64, plus slack)
-constexpr int NLMAX = 2048;              // newline capacity per tile (mean line >= 42 B at full tile size)
+constexpr int NLMAX = NTG_NLMAX;              // newline capacity per tile (mean line >= 42 B at full tile size)
 constexpr int SEG = 512;                 // long lines are cut into SEG-byte pieces
 constexpr int LONGMAX = TILE / SEG + 2;
 constexpr int NWK = NT;                  // threads that run the tile loop's cooperative phases
 constexpr uint64_t NONE = ~0ull;
 constexpr uint64_t INHDR = ~0ull - 1;
 
-enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4, FLAG_WS_BAIL = 8, FLAG_SPEC_MISS = 16 };
+enum : uint32_t { FLAG_PARSE_ERROR = 1, FLAG_NL_OVERFLOW = 2, FLAG_HALO_OVERFLOW = 4, FLAG_WS_BAIL = 8, FLAG_SPEC_MISS = 16, FLAG_FORMAT = 32 };
 
 // carried scan state (prefix over tiles)
 struct SState {
@@ -90,6 +104,9 @@ struct Params {
     uint32_t* ticket;
     unsigned long long* tallies;      // 16 x u64
     uint32_t* flags;
+    unsigned long long* err_key;       // first parse error of the stream: min over (start byte of the failing record << 2 | check order); ~0 = none
+    unsigned long long* fin;           // k_finalize: [0] error kind of an end-of-stream error, [1] its line (FASTA)
+    unsigned long long* reduce_buf;    // non-null: k_finalize copies the tallies (+ a "needs the host" count) into the all-reduce send buffer
     SState* final_state;
     uint32_t k, m, w;
     uint32_t tile_bytes;               // multiple of 256, <= TILE: sized so one tile holds about NT sequence lines
@@ -141,6 +158,19 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// First parse error: the host replays the stream truncated at the start of the failing record (records before it are
+// delivered, fastq.rs:243,253,277) and classifies the error there with the record scanner (parse.cuh).  `check` = order of
+// the reference's checks inside one record (0 start byte, 1 separator, 2 lengths, 3 end of stream).
+__host__ __device__ __forceinline__ void note_parse_error(unsigned long long* err_key, uint32_t& slow, uint64_t rec_start, uint32_t check) {
+    slow |= 1u;                                       // FLAG_PARSE_ERROR
+    const unsigned long long key = ((unsigned long long)rec_start << 2) | check;
+#ifdef __CUDA_ARCH__
+    atomicMin(err_key, key);
+#else
+    if (key < *err_key) *err_key = key;
+#endif
 }
 
 // ---- shared memory layout ------------------------------------------------------------------
@@ -946,9 +976,9 @@ __device__ __forceinline__ void halo_line_start(const uint8_t* __restrict__ sb, 
 // first four newline offsets (tile-relative), Cs = number of newlines in the tile, `pre` = the tile's exclusive prefix
 // (line roles come from its newline count, lines that began in earlier tiles from its last[] positions).  i <= Cs.
 // __host__ __device__: tests/cpp/test_walkers.cu checks it against a direct evaluation of the definition.
-__host__ __device__ __forceinline__ void first_lines_event(const uint8_t* __restrict__ bytes, uint64_t tile_start, const uint32_t* nl4, uint32_t Cs,
+__host__ __device__ __forceinline__ void first_lines_event(const uint8_t* __restrict__ bytes, uint64_t gmin, uint64_t tile_start, const uint32_t* nl4, uint32_t Cs,
                                                            uint32_t avail, bool line0_starts_here, const SState& pre, uint32_t i, Acc& acc,
-                                                           uint32_t& slow) {
+                                                           uint32_t& slow, unsigned long long* err_key) {
     const uint32_t ord0 = (uint32_t)(pre.count & 3);
     auto nl = [&](uint32_t j) -> uint64_t { return tile_start + nl4[j]; };                        // j < min(Cs, 4)
     auto prev_nl = [&](uint32_t back) -> uint64_t {                                               // `back` newlines before newline i
@@ -958,15 +988,18 @@ __host__ __device__ __forceinline__ void first_lines_event(const uint8_t* __rest
     };
     auto cr_before = [&](uint64_t q, uint64_t prevq) -> uint32_t {                                // trim_cr on the line (prevq, q)
         const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
-        return (q > ls && bytes[q - 1] == '\r') ? 1u : 0u;
+        if (q <= ls) return 0u;
+        if (q - 1 < gmin) { slow |= FLAG_HALO_OVERFLOW; return 0u; }                              // (a streamed window that no longer holds the byte)
+        return bytes[q - 1] == '\r' ? 1u : 0u;
     };
     const uint32_t role = (ord0 + i) & 3;
+    auto rec_start = [&]() -> uint64_t { const uint64_t p = prev_nl(role + 1); return p == NONE ? 0 : p + 1; };   // line i - role starts the record
     const uint64_t s = i ? nl(i - 1) + 1 : tile_start;
     const bool starts = (i > 0 || line0_starts_here) && (s - tile_start) < avail;
     if (starts) {
         const uint8_t c = bytes[s];
-        if (role == 0 && c != '@') slow |= FLAG_PARSE_ERROR;
-        if (role == 2 && c != '+') slow |= FLAG_PARSE_ERROR;
+        if (role == 0 && c != '@') note_parse_error(err_key, slow, s, 0);
+        if (role == 2 && c != '+') note_parse_error(err_key, slow, rec_start(), 1);
     }
     if (i < Cs) {
         const uint64_t q = nl(i);
@@ -976,11 +1009,11 @@ __host__ __device__ __forceinline__ void first_lines_event(const uint8_t* __rest
             acc.n_bases += (q - ls) - cr_before(q, p1);
         } else if (role == 3) {
             const uint64_t q2 = prev_nl(1), q1 = prev_nl(2), q0 = prev_nl(3);
-            if (q2 == NONE || q1 == NONE || q0 == NONE) slow |= FLAG_PARSE_ERROR;
+            if (q2 == NONE || q1 == NONE || q0 == NONE) note_parse_error(err_key, slow, 0, 0);    // inconsistent state: replay from the start
             else {
                 const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
                 const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
-                if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;
+                if (seq_len != qual_len) note_parse_error(err_key, slow, rec_start(), 2);
                 acc.n_records++;
             }
         }
@@ -999,7 +1032,7 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
     if (S.pend_guess != ord0) slow |= FLAG_SPEC_MISS;
     const uint32_t Cs = S.pend_cs;
     if (lane < 4 && lane <= Cs)
-        first_lines_event(P.bytes, t * (uint64_t)P.tile_bytes, S.pend_nl4, Cs, S.pend_avail, S.pend_line0 != 0, pre, lane, acc, slow);
+        first_lines_event(P.bytes, P.gmin, t * (uint64_t)P.tile_bytes, S.pend_nl4, Cs, S.pend_avail, S.pend_line0 != 0, pre, lane, acc, slow, P.err_key);
     __syncwarp();
     if (lane == 0) S.pend_valid = 0;
     __syncwarp();
@@ -1008,7 +1041,7 @@ __device__ __noinline__ void resolve_pending(const Params& P, Smem& S, uint32_t 
 
 
 template <int KW, bool MINI, int W, int FK, int FM>
-__global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const uint64_t tile_begin, const uint64_t tile_end,
                                                  const uint32_t epoch, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -1030,6 +1063,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 #if NTG_STATS
     const long long st_t0 = clock64();
     long long st_lb = 0, st_wait = 0, st_walk = 0, st_mark = 0; uint32_t st_nlb = 0;
+    long long st_p0 = 0, st_p1 = 0, st_p2 = 0, st_ph = 0;      // NTG_STATS == 2: thread 0's cycles in P0 / P1 / P2 (replace the look-back counters)
 #endif
     Acc acc;
     const uint8_t* sb = S.tile;
@@ -1055,6 +1089,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         const uint32_t bulk = avail & ~15u;
 
         if (tid == 0) S.n_long = 0;
+#if NTG_STATS
+        st_ph = clock64();
+#endif
         // ---- P0: stage the tile (+ back halo) with one bulk async copy
         if (tid == 0 && halo + bulk) {
             mbar_expect_tx(&S.bar, halo + bulk);
@@ -1064,6 +1101,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         if (t == 0) for (int i = tid; i < HALO; i += NWK) S.halo[i] = 0;
         if (halo + bulk) { mbar_wait(&S.bar, parity); parity ^= 1; }
         tile_sync();
+#if NTG_STATS
+        { const long long c = clock64(); st_p0 += c - st_ph; st_ph = c; }
+#endif
 
         // ---- P1: newline scan, 256 B rows, row = round * NT + tid (rotated word order: conflict-free LDS.32)
         const uint32_t nrows = TB / ROWB;
@@ -1075,11 +1115,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             const uint32_t rowi = rd * NTW + tid;
             if (tid < NTW && rowi < nrows) scan_row(reinterpret_cast<const uint32_t*>(S.tile) + rowi * ROWW, lane, cnt[rd], wmask[rd]);
         }
+#if NTG_STATS
+        { const long long c = clock64(); st_p1 += c - st_ph; st_ph = c; }
+#endif
         // ---- P2: ordered newline list (rows are ordered round-major: one scan of the packed per-round counts)
         // The two per-round counts share one u32 for a single block scan: round 0 covers NTW rows (at most NTW * 256 = 73 728
         // newlines: 17 bits), round 1 the remaining TILE / 256 - NTW rows (at most 12 288: 14 bits) -> 17 + 15 bits, no wrap
         // even for a tile made of newlines (a run of blank lines is valid FASTA / FASTQ tail).
-        static_assert(MAXROUNDS == 2 && NTW * ROWB < (1 << 17) && (TILE / ROWB - NTW) * ROWB < (1 << 15), "packed scan: 17 + 15 bits");
+        static_assert(MAXROUNDS == 2 && NTW * ROWB < (1 << 17) && (TILE / ROWB - NTW) * ROWB < (1 << 15) && TILE / ROWB >= NTW, "packed scan: 17 + 15 bits");
         uint32_t Cpacked;
         const uint32_t offp = block_excl_scan(cnt[0] | (cnt[1] << 17), &Cpacked, S.warp_tmp[0]);
         const uint32_t C0 = Cpacked & 0x1FFFFu, C = C0 + (Cpacked >> 17);
@@ -1104,6 +1147,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
             }
         }
         tile_sync();
+#if NTG_STATS
+        { const long long c = clock64(); st_p2 += c - st_ph; st_ph = c; }
+#endif
         const uint32_t Cs = overflow ? 0 : C;                          // lines are only interpreted when the list is complete
         // line i (0..Cs) spans (nl[i-1], nl[i]) ; helpers on tile-relative coordinates
         auto line_start_rel = [&](uint32_t i) -> int { return i ? (int)S.nl[i - 1] + 1 : 0; };   // for i == 0: start of the in-tile fragment
@@ -1201,7 +1247,9 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         };
         auto cr_before = [&](uint64_t q, uint64_t prevq) -> uint32_t {      // trim_cr on the line (prevq, q)
             const uint64_t ls = prevq == NONE ? 0 : prevq + 1;
-            return (q > ls && byte_at(P, sb, tile_start, halo, q - 1) == '\r') ? 1u : 0u;
+            if (q <= ls) return 0u;
+            if (q - 1 + halo < tile_start && q - 1 < P.gmin) { slow |= FLAG_HALO_OVERFLOW; return 0u; }   // (streamed window no longer holds it)
+            return byte_at(P, sb, tile_start, halo, q - 1) == '\r' ? 1u : 0u;
         };
         // warm-up bound of a fragment of line i: the line start (FASTQ) / the sequence-region start (FASTA)
         auto fastq_bound = [&](uint32_t i, int a, int& lo, bool& lo_exact) {
@@ -1242,9 +1290,10 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                 const uint32_t role = (ord0 + i) & 3;                     // 0 header, 1 sequence, 2 separator, 3 quality
                 const int s = line_start_rel(i);
                 const bool starts = (i > 0 || line0_starts_here) && (uint32_t)s < avail;
+                auto rec_start = [&]() -> uint64_t { const uint64_t p = prev_nl(i, role + 1); return p == NONE ? 0 : p + 1; };
                 if (starts) {
-                    if (role == 0 && sb[s] != '@') slow |= FLAG_PARSE_ERROR;
-                    if (role == 2 && sb[s] != '+') slow |= FLAG_PARSE_ERROR;
+                    if (role == 0 && sb[s] != '@') note_parse_error(P.err_key, slow, tile_start + (uint64_t)s, 0);
+                    if (role == 2 && sb[s] != '+') note_parse_error(P.err_key, slow, rec_start(), 1);
                 }
                 if (i < Cs) {                                             // the line ends in this tile at newline q
                     const uint64_t q = tile_start + S.nl[i];
@@ -1254,11 +1303,11 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
                         acc.n_bases += (q - ls) - cr_before(q, p1);
                     } else if (role == 3) {
                         const uint64_t q2 = prev_nl(i, 1), q1 = prev_nl(i, 2), q0 = prev_nl(i, 3);
-                        if (q2 == NONE || q1 == NONE || q0 == NONE) slow |= FLAG_PARSE_ERROR;   // inconsistent state
+                        if (q2 == NONE || q1 == NONE || q0 == NONE) note_parse_error(P.err_key, slow, 0, 0);   // inconsistent state
                         else {
                             const uint64_t seq_len = (q1 - q0 - 1) - cr_before(q1, q0);
                             const uint64_t qual_len = (q - q2 - 1) - cr_before(q, q2);
-                            if (seq_len != qual_len) slow |= FLAG_PARSE_ERROR;
+                            if (seq_len != qual_len) note_parse_error(P.err_key, slow, rec_start(), 2);
                             acc.n_records++;
                         }
                     }
@@ -1372,7 +1421,11 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
         const unsigned long long life = (unsigned long long)(clock64() - st_t0);
         if (tid == 0) { atomicAdd(&P.tallies[9], life); atomicMax(&P.tallies[12], life);
                         atomicAdd(&P.tallies[14], (unsigned long long)st_wait); atomicAdd(&P.tallies[15], (unsigned long long)st_walk); }
+#if NTG_STATS == 2
+        if (tid == 0) { atomicAdd(&P.tallies[10], (unsigned long long)st_p0); atomicAdd(&P.tallies[11], (unsigned long long)st_p1); atomicAdd(&P.tallies[6], (unsigned long long)st_p2); }   // ([6] = n_query: unused without a query)
+#else
         if (tid == NTW) { atomicAdd(&P.tallies[10], (unsigned long long)st_lb); atomicAdd(&P.tallies[11], (unsigned long long)st_nlb); }
+#endif
     }
 #endif
     // ---- P4: block reduction of the register tallies, 9 atomics per CTA
@@ -1396,32 +1449,52 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const Params P, const uint64_t 
 // ---- end-of-stream rules, one thread (fastq.rs:337-356, fasta.rs:200-216,348-356) ----------------
 __global__ void k_finalize(const Params P) {
     const SState st = *P.final_state;
-    uint32_t err = 0;
+    uint32_t err = 0, slow = 0;
+    auto byte = [&](uint64_t p) -> uint8_t {                        // (a streamed window holds the stream's tail only)
+        if (p < P.gmin || p >= P.n) { slow |= FLAG_HALO_OVERFLOW; return 0; }
+        return P.bytes[p];
+    };
     if (P.format == NTG_FMT_FASTQ) {
         const uint32_t r = (uint32_t)(st.count & 3);
         const bool have_complete = st.count >= 4;
         uint64_t start = 0;
         if (have_complete) start = st.last[r] + 1;                 // behind the 4th newline of the last complete record
-        auto trim = [&](uint64_t b, uint64_t e) { return (e > b && P.bytes[e - 1] == '\r') ? e - 1 : e; };
+        auto trim = [&](uint64_t b, uint64_t e) { return (e > b && byte(e - 1) == '\r') ? e - 1 : e; };
         if (r == 3) {                                              // last record without trailing newline
             const uint64_t seq = st.last[2] + 1, sep = st.last[1] + 1, qual = st.last[0] + 1, end = P.n;
-            if (P.bytes[start] != '@' || P.bytes[sep] != '+' || trim(seq, sep - 1) - seq != trim(qual, end) - qual) err = 1;
+            if (byte(start) != '@' || byte(sep) != '+' || trim(seq, sep - 1) - seq != trim(qual, end) - qual) err = 1;
             else atomicAdd(&P.tallies[0], 1ull);
         } else {
             uint64_t ls = start;
             for (uint32_t i = 0; i <= r; i++) {                     // leftover must be empty / "\r" lines only
                 const uint64_t le = i < r ? st.last[r - 1 - i] : P.n;
                 const uint64_t len = le - ls;
-                if (len > 1 || (len == 1 && P.bytes[ls] != '\r')) err = 1;
+                if (len > 1 || (len == 1 && byte(ls) != '\r')) err = 1;
                 ls = le + 1;
             }
         }
+        if (err) note_parse_error(P.err_key, slow, start, 3);       // the host replays [0, start) and classifies the record at `start`
     } else {
-        // FASTA: the last record needs a pushed newline (one that is not the final byte)
-        if (st.hdr == INHDR || st.hdr == NONE || st.hdr == P.n - 1) err = 1;
-        P.tallies[0] = st.n_starts;
+        // FASTA: the last record needs a pushed newline (one that is not the final byte); without one it is an UnexpectedEnd
+        // (fasta.rs:205-213,348-356) and is not delivered.  Its header line is the last line of the stream: nothing of it was tallied.
+        const bool bad = st.hdr == INHDR || st.hdr == NONE || st.hdr == P.n - 1;
+        P.tallies[0] = st.n_starts - (bad && st.n_starts ? 1 : 0);
+        if (bad) {
+            slow |= FLAG_PARSE_ERROR;
+            P.fin[0] = NTG_EUNEXPECTED_END;
+            P.fin[1] = 1 + st.count - ((st.hdr != INHDR && st.hdr != NONE) ? 1 : 0);    // line of that header: newlines before it + 1
+            P.fin[2] = st.n_starts ? st.n_starts - 1 : 0;                              // its record index
+        }
     }
-    if (err) atomicOr(P.flags, (uint32_t)FLAG_PARSE_ERROR);
+    // (the resident entry point caches the sniffed format per buffer: a buffer whose content changed format is caught here)
+    if (P.gmin == 0 && P.n && P.bytes[0] != (P.format == NTG_FMT_FASTQ ? '@' : '>')) slow |= FLAG_FORMAT;
+    if (slow) atomicOr(P.flags, slow);
+    if (P.reduce_buf) {
+#pragma unroll 1
+        for (int i = 0; i < 9; i++) P.reduce_buf[i] = P.tallies[i];
+        P.reduce_buf[9] = *P.flags ? 1ull : 0ull;                  // ranks whose result needs the host (error replay, exact path)
+        for (int i = 10; i < 16; i++) P.reduce_buf[i] = 0;
+    }
 }
 
 // ---- exact fallback: one thread per parsed record walks its raw_seq from global memory ---------

@@ -1,34 +1,72 @@
 // fused_host.cuh — host orchestration of the fused tallies path.  Part of the unity build.
+//
+// One pass = a sequence of LAUNCHES of fused::k_fused over consecutive tile ranges of one byte stream.  The look-back state
+// (slot ring, generations) carries across launches, so a stream can be fed segment by segment through two/three device
+// buffers of SEG bytes: inputs of any size run in bounded device memory (the reference streams through a growable
+// buffer: src/parser/fastq.rs:312-384, src/parser/utils.rs:34-49).  Each launch writes its own control block (tallies,
+// flags, first-error key); the host adds the blocks up.
+//
+// Error semantics (iterator: records before the first error are delivered, fastq.rs:243,253,277): the kernel reports the
+// start byte E of the first failing record; the host REPLAYS the stream truncated at E (a clean end of stream) and
+// classifies the error with the record scanner on a window at E.  Inputs the single pass cannot take (newline-dense
+// tiles, whitespace runs longer than the halo) go to the exact record-table path, window by window.
 #pragma once
 #include "fused.cuh"
 #include "parse.cuh"
 
-struct FusedControl {           // device-resident control block, zeroed per call
+struct LaunchCtl {                    // device-resident control block of one launch (mirrored in pinned host memory)
     unsigned long long tallies[16];
-    uint32_t flags;
-    uint32_t tickets[59];       // one ticket per kernel launch of a call (chunked feeds use several)
+    unsigned long long err_key;       // ~0 = no parse error
+    unsigned long long fin[4];        // k_finalize: [0] kind of an end-of-stream error (FASTA), [1] its line, [2] its record index
+    uint32_t flags, ticket;
+    uint32_t pad[4];
 };
-static_assert(sizeof(FusedControl) == 128 + 4 + 59 * 4, "layout");
-constexpr int FUSED_MAX_LAUNCHES = 59;
+static_assert(sizeof(LaunchCtl) == 192, "layout");
+constexpr int NCTL = 8;                  // control blocks in flight (a streamed pass keeps at most three launches unchecked)
+constexpr int CTL_REDO = NCTL - 1;       // block reserved for replays
 constexpr uint32_t SLOT_SHIFT = 16;      // 65 536 slots (16 MiB) + 65 536 words: far more than the tiles in flight plus the look-back reach
+constexpr size_t STREAM_BACK = size_t(1) << 20;      // bytes of history kept in front of every streamed segment (lines that cross into it)
+constexpr size_t STREAM_SEG = size_t(64) << 20;      // segment size of streamed passes (rounded down to whole tiles)
+constexpr int NSEG = 3;                              // device segments: a flagged launch and its neighbours stay intact until checked
+
+struct PassResult {                   // sum over the launches of one pass
+    unsigned long long tallies[16] = {};
+    unsigned long long err_key = ~0ull;
+    unsigned long long fin[4] = {};
+    uint32_t flags = 0;
+    void add(const LaunchCtl& c) {
+        for (int i = 0; i < 16; i++) tallies[i] += c.tallies[i];
+        if (c.err_key < err_key) err_key = c.err_key;
+        if (c.fin[0]) for (int i = 0; i < 4; i++) fin[i] = c.fin[i];
+        flags |= c.flags;
+    }
+};
 
 struct FusedState {
     fused::TileSlot* slots = nullptr;        // ring of 1 << SLOT_SHIFT tile slots + look-back words (never cleared: generations)
     unsigned long long* cw = nullptr;
-    FusedControl* ctrl = nullptr;
     fused::SState* final_state = nullptr;
-    FusedControl* h_ctrl = nullptr;          // pinned
+    LaunchCtl* ctl = nullptr;                // NCTL blocks, device
+    LaunchCtl* h_ctl = nullptr;              // NCTL blocks, pinned
+    cudaEvent_t ev_done[NCTL] = {};
+    cudaEvent_t ev_copy[NSEG] = {};
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     uint32_t epoch = 0;
+    uint64_t epoch_tiles = 0;                // tiles of the pass that owns `epoch`
     int max_ctas = 0;
-    // pending call
-    bool pending = false;
+    uint8_t* seg[NSEG] = {};                 // streamed passes: STREAM_BACK + seg_cap bytes each
+    size_t seg_cap = 0;
+    unsigned long long* reduce_buf = nullptr;   // 16 x u64: send/receive buffer of the in-stream tallies all-reduce
+    unsigned long long* h_reduce = nullptr;     // pinned mirror
+    // resident call pending between enqueue and collect
+    bool pending = false, pending_reduce = false;
     fused::Params P{};
     ntg_tally_config cfg{};
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_ready = nullptr;
-    cudaEvent_t ev_chunk[FUSED_MAX_LAUNCHES] = {};
-    uint8_t* feed_buf = nullptr; size_t feed_cap = 0;   // device staging for host feeds
-    const uint8_t* host_bytes = nullptr;                // when the call was fed from host memory
-    uint32_t general_tile_bytes = 0;                    // tile size for a re-run without speculation
+    int format = 0;
+    uint32_t general_tile_bytes = 0;
+    // sniff cache of the resident entry point: (pointer, size) -> format + tile size, verified on the device (byte 0)
+    uint64_t sniff_ptr = 0; size_t sniff_n = 0; int sniff_format = 0; uint32_t sniff_tile = 0;
+    uint64_t pend_dptr = 0; size_t pend_n = 0;
 };
 
 typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
@@ -58,17 +96,19 @@ static int fused_init(ntg_ctx* ctx) {
     if (ctx->fused) return NTG_OK;
     auto* st = new FusedState();
     ctx->fused = st;
-    NTG_CUDA(ctx, cudaMalloc((void**)&st->ctrl, sizeof(FusedControl)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->ctl, NCTL * sizeof(LaunchCtl)));
+    NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_ctl, NCTL * sizeof(LaunchCtl)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->final_state, sizeof(fused::SState)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->slots, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->cw, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->reduce_buf, 16 * sizeof(unsigned long long)));
+    NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_reduce, 16 * sizeof(unsigned long long)));
     NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot), ctx->stream));
     NTG_CUDA(ctx, cudaMemsetAsync(st->cw, 0, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long), ctx->stream));
-    NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_ctrl, sizeof(FusedControl)));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k0));
     NTG_CUDA(ctx, cudaEventCreate(&st->ev_k1));
-    NTG_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_ready, cudaEventDisableTiming));
-    for (auto& e : st->ev_chunk) NTG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : st->ev_done) NTG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : st->ev_copy) NTG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     using namespace fused;
 #define NTG_X(k) (fused_kernel_t)k,
     fused_kernel_t ks[] = {NTG_FUSED_KERNELS(NTG_X)};
@@ -87,11 +127,13 @@ static int fused_init(ntg_ctx* ctx) {
 static void fused_destroy(ntg_ctx* ctx) {
     FusedState* st = ctx->fused;
     if (!st) return;
-    cudaFree(st->slots); cudaFree(st->cw); cudaFree(st->ctrl); cudaFree(st->final_state); cudaFreeHost(st->h_ctrl); cudaFree(st->feed_buf);
+    cudaFree(st->slots); cudaFree(st->cw); cudaFree(st->ctl); cudaFree(st->final_state); cudaFreeHost(st->h_ctl);
+    cudaFree(st->reduce_buf); cudaFreeHost(st->h_reduce);
+    for (auto& p : st->seg) cudaFree(p);
     if (st->ev_k0) cudaEventDestroy(st->ev_k0);
     if (st->ev_k1) cudaEventDestroy(st->ev_k1);
-    if (st->ev_ready) cudaEventDestroy(st->ev_ready);
-    for (auto& e : st->ev_chunk) if (e) cudaEventDestroy(e);
+    for (auto& e : st->ev_done) if (e) cudaEventDestroy(e);
+    for (auto& e : st->ev_copy) if (e) cudaEventDestroy(e);
     delete st; ctx->fused = nullptr;
 }
 
@@ -105,7 +147,6 @@ static int check_tally_cfg(ntg_ctx* ctx, const ntg_tally_config* cfg) {
     return NTG_OK;
 }
 
-// Prepare a call over n device-resident bytes; launches nothing yet.
 // Tile size: about NT sequence lines per tile, so that every walker thread gets exactly one line.
 // `sample` = the first bytes of the input (host copy), used to estimate the line period.
 static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
@@ -128,25 +169,21 @@ static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
     return tb;
 }
 
-static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes,
-                       bool allow_spec = true) {
+// Start a pass: a fresh range of slot generations and the launch-invariant kernel parameters.
+static int fused_begin_pass(ntg_ctx* ctx, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool allow_spec, uint64_t max_tiles) {
     NTG_TRY(fused_init(ctx));
     FusedState* st = ctx->fused;
-    if (st->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is already pending: collect it first");
-    st->general_tile_bytes = tile_bytes;
-    if ((reinterpret_cast<uintptr_t>(dbytes) & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
-    const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
-    // a fresh range of slot generations for this call: the previous call used epoch .. epoch + (its tiles >> SLOT_SHIFT)
-    st->epoch = (st->epoch + 1 + (uint32_t)(st->P.num_tiles >> SLOT_SHIFT)) & 0x3FFFFFFFu;
-    if (st->epoch + (num_tiles >> SLOT_SHIFT) + 2 >= 0x3FFFFFFFull) {       // (once per 2^30 calls) start the generations over
+    // the previous pass used epoch .. epoch + (its tiles >> SLOT_SHIFT)
+    st->epoch = (st->epoch + 1 + (uint32_t)(st->epoch_tiles >> SLOT_SHIFT)) & 0x3FFFFFFFu;
+    if (st->epoch + (max_tiles >> SLOT_SHIFT) + 2 >= 0x3FFFFFFFull) {       // (once per 2^30 passes) start the generations over
         NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot), ctx->stream));
         NTG_CUDA(ctx, cudaMemsetAsync(st->cw, 0, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long), ctx->stream));
         st->epoch = 1;
     }
-    NTG_CUDA(ctx, cudaMemsetAsync(st->ctrl, 0, sizeof(FusedControl), ctx->stream));
+    st->epoch_tiles = max_tiles;
     fused::Params& P = st->P;
-    P.bytes = dbytes; P.n = n; P.num_tiles = num_tiles; P.slots = st->slots; P.cw = st->cw; P.slot_mask = (1u << SLOT_SHIFT) - 1; P.slot_shift = SLOT_SHIFT; P.gmin = 0; P.ticket = nullptr;
-    P.tallies = st->ctrl->tallies; P.flags = &st->ctrl->flags; P.final_state = st->final_state;
+    P = fused::Params{};
+    P.slots = st->slots; P.cw = st->cw; P.slot_mask = (1u << SLOT_SHIFT) - 1; P.slot_shift = SLOT_SHIFT; P.final_state = st->final_state;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
     P.spec = (allow_spec && format == NTG_FMT_FASTQ && !(cfg->flags & NTG_TALLY_NO_SPECULATION)) ? 1 : 0;
     P.q_lo = P.q_hi = 0;
@@ -155,90 +192,282 @@ static int fused_begin(ntg_ctx* ctx, const uint8_t* dbytes, size_t n, int format
             P.q_hi = (P.q_hi << 2) | (P.q_lo >> 62);
             P.q_lo = (P.q_lo << 2) | host_luts().code[cfg->query[i]];
         }
-    st->cfg = *cfg;
-    st->pending = true;
-    return NTG_OK;
-}
-// Launch the fused kernel over tiles [tb, te) as launch number `li` of this call.
-static int fused_launch(ntg_ctx* ctx, uint64_t tb, uint64_t te, int li) {
-    FusedState* st = ctx->fused;
-    if (te <= tb) return NTG_OK;
-    uint64_t nt = te - tb;
-    unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
-    fused_kernel_t kf = pick_fused_kernel(st->P.k, st->P.m, st->P.has_query != 0);
-    kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(st->P, tb, te, st->epoch, &st->ctrl->tickets[li]);
-    ctx->launches++;
-    NTG_CUDA(ctx, cudaGetLastError());
-    return NTG_OK;
-}
-static int fused_finish_enqueue(ntg_ctx* ctx) {
-    FusedState* st = ctx->fused;
-    fused::k_finalize<<<1, 1, 0, ctx->stream>>>(st->P);
-    ctx->launches++;
-    NTG_CUDA(ctx, cudaGetLastError());
-    NTG_CUDA(ctx, cudaMemcpyAsync(st->h_ctrl, st->ctrl, sizeof(FusedControl), cudaMemcpyDeviceToHost, ctx->stream));
+    st->cfg = *cfg; st->format = format; st->general_tile_bytes = tile_bytes;
     return NTG_OK;
 }
 
-// forward: device-side parse used by the exact fallback (parse.cuh)
-static int run_parse_device(ntg_ctx* ctx, const uint8_t* host_bytes, const uint8_t* dbytes, size_t n, ntg_records** out,
-                            DevBuf<ntg_record>* keep_drecs);
-
-static void tallies_from_ctrl(const FusedControl* c, ntg_tallies* out) {
-    std::memset(out, 0, sizeof(*out));
-    out->n_records = c->tallies[0]; out->n_bases = c->tallies[1]; out->n_kmers = c->tallies[2]; out->n_not_rc = c->tallies[3];
-    out->kmer_sum_lo = c->tallies[4]; out->kmer_sum_hi = c->tallies[5]; out->n_query = c->tallies[6];
-    out->n_minimizers = c->tallies[7]; out->minimizer_sum = c->tallies[8];
-    for (int i = 0; i < 5; i++) out->reserved[2 + i] = c->tallies[9 + i];   // producer cycle accounting of the warp-specialised kernel
-    out->reserved[5] = c->tallies[14]; out->reserved[6] = c->tallies[15];   // (walker wait / work cycles replace two of them)
-}
-
-static int fused_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_error* err, float* fused_kernel_ms) {
+// Enqueue one launch of the pass over tiles [tb, te): `base` is the (virtual) address of stream byte 0, `gmin` the lowest
+// stream position readable through it, `n_vis` the number of stream bytes that exist for this launch (the end of its last
+// tile, or the stream length when `final`).  Results go to control block `ci` and its pinned mirror; ev_done[ci] fires
+// when the mirror is valid.  `reduce` (final launches): k_finalize leaves the tallies in the all-reduce send buffer.
+static int fused_enqueue_launch(ntg_ctx* ctx, const uint8_t* base, uint64_t gmin, uint64_t n_vis, uint64_t tb, uint64_t te, bool final, int ci,
+                                bool reduce = false) {
     FusedState* st = ctx->fused;
-    if (!st || !st->pending) return ntg_set_error(ctx, NTG_EINVAL, "no pending tally call");
-    st->pending = false;
-    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (fused_kernel_ms) NTG_CUDA(ctx, cudaEventElapsedTime(fused_kernel_ms, st->ev_k0, st->ev_k1));
-    if (err) std::memset(err, 0, sizeof(*err));
-    if (err) err->format = st->P.format;
-    uint32_t fast_flags = st->h_ctrl->flags;
-    if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); return NTG_OK; }
-    const uint32_t ws_flags = (fast_flags & fused::FLAG_SPEC_MISS) ? fast_flags : 0;
-    if (fast_flags & fused::FLAG_SPEC_MISS) {
-        // a speculated FASTQ line phase was wrong: one plain pass (no speculation) over the same bytes
-        const ntg_tally_config cfg = st->cfg;
-        NTG_TRY(fused_begin(ctx, st->P.bytes, st->P.n, st->P.format, &cfg, st->general_tile_bytes, /*allow_spec=*/false));
-        int s2 = fused_launch(ctx, 0, st->P.num_tiles, 0);
-        if (s2 == NTG_OK) s2 = fused_finish_enqueue(ctx);
-        st->pending = false;
-        NTG_TRY(s2);
-        NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        fast_flags = st->h_ctrl->flags;
-        if (fast_flags == 0) { tallies_from_ctrl(st->h_ctrl, out); out->reserved[1] = ws_flags; return NTG_OK; }
-    }
-
-    // ---- exact fallback: record table on the device, then one thread per delivered record
-    ntg_records* recs = nullptr;
-    DevBuf<ntg_record> drecs;
-    NTG_TRY(run_parse_device(ctx, st->host_bytes, st->P.bytes, st->P.n, &recs, &drecs));
-    if (err) *err = recs->error;
-    NTG_CUDA(ctx, cudaMemsetAsync(st->ctrl, 0, sizeof(FusedControl), ctx->stream));
-    if (recs->n_records) {
-        unsigned grid = (unsigned)((recs->n_records + 127) / 128);
-        if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
-        if (st->P.k > 32) fused::k_tally_records<2, false><<<grid, 128, 0, ctx->stream>>>(st->P, drecs.p, recs->n_records);
-        else if (st->P.m == 0) fused::k_tally_records<1, false><<<grid, 128, 0, ctx->stream>>>(st->P, drecs.p, recs->n_records);
-        else fused::k_tally_records<1, true><<<grid, 128, 0, ctx->stream>>>(st->P, drecs.p, recs->n_records);
+    LaunchCtl* c = st->ctl + ci;
+    NTG_CUDA(ctx, cudaMemsetAsync(c, 0, sizeof(LaunchCtl), ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(&c->err_key, 0xFF, sizeof(c->err_key), ctx->stream));
+    fused::Params P = st->P;
+    P.bytes = base; P.gmin = gmin; P.n = n_vis; P.num_tiles = final ? te : (uint64_t(1) << 62);
+    P.tallies = c->tallies; P.flags = &c->flags; P.err_key = &c->err_key; P.fin = c->fin; P.ticket = nullptr;
+    P.reduce_buf = reduce ? st->reduce_buf : nullptr;
+    if (te > tb) {
+        const uint64_t nt = te - tb;
+        const unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
+        fused_kernel_t kf = pick_fused_kernel(P.k, P.m, P.has_query != 0);
+        kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(P, tb, te, st->epoch, &c->ticket);
         ctx->launches++;
+        NTG_CUDA(ctx, cudaGetLastError());
     }
-    cudaError_t e = cudaGetLastError();
-    if (!e) e = cudaMemcpyAsync(st->h_ctrl, st->ctrl, sizeof(FusedControl), cudaMemcpyDeviceToHost, ctx->stream);
-    if (!e) e = cudaStreamSynchronize(ctx->stream);
-    ntg_records_free(recs);
-    if (e) return ntg_set_error(ctx, NTG_ECUDA, "fallback: %s", cudaGetErrorString(e));
-    tallies_from_ctrl(st->h_ctrl, out);
-    out->reserved[1] = ws_flags;
-    out->reserved[0] = fast_flags;          // why the exact path ran: 1 parse error, 2 newline-dense tile, 4 whitespace run > halo
+    if (final) {
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_k1, ctx->stream));
+        fused::k_finalize<<<1, 1, 0, ctx->stream>>>(P);
+        ctx->launches++;
+        NTG_CUDA(ctx, cudaGetLastError());
+    }
+    if (!reduce) {
+        NTG_CUDA(ctx, cudaMemcpyAsync(st->h_ctl + ci, c, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_done[ci], ctx->stream));
+    }
+    return NTG_OK;
+}
+
+// ---- a pass over bytes resident in device memory: one launch -----------------------------------------------------
+static int pass_resident(ntg_ctx* ctx, const uint8_t* dbytes, uint64_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec,
+                         PassResult* out) {
+    FusedState* st = ctx->fused;
+    const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
+    NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, num_tiles));
+    NTG_TRY(fused_enqueue_launch(ctx, dbytes, 0, n, 0, num_tiles, true, 0));
+    NTG_CUDA(ctx, cudaEventSynchronize(st->ev_done[0]));
+    *out = PassResult{};
+    out->add(st->h_ctl[0]);
+    return NTG_OK;
+}
+
+// ---- a pass over a host byte stream fed in segments ------------------------------------------------------------------
+// Device memory: NSEG buffers of STREAM_BACK + seg_cap bytes.  Launch L uses buffer L % NSEG: its data behind STREAM_BACK
+// bytes of history copied from the tail of the previous buffer (lines and records that cross into the segment).
+struct SegmentFeed {
+    ntg_ctx* ctx = nullptr;
+    FusedState* st = nullptr;
+    uint32_t TB = 0;
+    uint64_t L = 0;                  // launches submitted
+    uint64_t next_tile = 0;
+    size_t prev_len = 0;
+    uint64_t checked = 0;            // launches whose control block has been read back
+    struct Rec { uint64_t tb, te, n_vis; size_t len; bool final; } recs[NCTL] = {};
+
+    int open(ntg_ctx* c, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec) {
+        ctx = c;
+        NTG_TRY(fused_init(ctx));
+        st = ctx->fused;
+        TB = tile_bytes;
+        if (!st->seg[0]) {
+            st->seg_cap = STREAM_SEG + fused::TILE;
+            for (auto& p : st->seg)
+                if (cudaMalloc((void**)&p, STREAM_BACK + st->seg_cap) != cudaSuccess) { cudaGetLastError(); return ntg_set_error(ctx, NTG_ENOMEM, "device segment allocation failed"); }
+        }
+        NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, uint64_t(1) << 40));
+        // the copy stream must not overwrite the segments while kernels of an earlier call still read them
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_copy[0], ctx->stream));
+        NTG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, st->ev_copy[0], 0));
+        return NTG_OK;
+    }
+    uint64_t seg_tiles() const { return STREAM_SEG / TB; }
+    // Submit the next `len` stream bytes (whole tiles unless final) from host memory.  Before buffer L % NSEG is reused
+    // the launch that used it (L - NSEG) must have been checked: `check(j, ctl)` is called for every launch in order.
+    template <typename Check>
+    int submit(const uint8_t* src, size_t len, bool final, uint64_t n_total, Check&& check) {
+        if (len > st->seg_cap) return ntg_set_error(ctx, NTG_EINVAL, "segment larger than the device segment buffer");
+        while (L >= (uint64_t)(NSEG - 1) && checked + (NSEG - 1) <= L) NTG_TRY(check_next(check));      // frees buffer L % NSEG
+        const int b = (int)(L % NSEG), pb = (int)((L + NSEG - 1) % NSEG), ci = (int)(L % (NCTL - 1));
+        uint8_t* buf = st->seg[b];
+        if (L > 0) NTG_CUDA(ctx, cudaMemcpyAsync(buf, st->seg[pb] + prev_len, STREAM_BACK, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        if (len) NTG_CUDA(ctx, cudaMemcpyAsync(buf + STREAM_BACK, src, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_copy[b], ctx->copy_stream));
+        NTG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->ev_copy[b], 0));
+        const uint64_t tb = next_tile, start = tb * (uint64_t)TB;
+        const uint64_t te = final ? (n_total + TB - 1) / TB : tb + len / TB;
+        const uint64_t n_vis = final ? n_total : te * (uint64_t)TB;
+        const uint64_t gmin = start > STREAM_BACK ? start - STREAM_BACK : 0;
+        if (L == 0) NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
+        NTG_TRY(fused_enqueue_launch(ctx, buf + STREAM_BACK - start, gmin, n_vis, tb, te, final, ci));
+        recs[ci] = Rec{tb, te, n_vis, len, final};
+        prev_len = len; next_tile = te; L++;
+        return NTG_OK;
+    }
+    template <typename Check>
+    int check_next(Check&& check) {
+        const int ci = (int)(checked % (NCTL - 1));
+        NTG_CUDA(ctx, cudaEventSynchronize(st->ev_done[ci]));
+        const uint64_t j = checked++;
+        return check(j, st->h_ctl[ci]);
+    }
+    template <typename Check>
+    int drain(Check&& check) {
+        while (checked < L) NTG_TRY(check_next(check));
+        return NTG_OK;
+    }
+    // device address of stream byte `g` while the launch that carried it is still resident (one of the last NSEG launches)
+    const uint8_t* device_addr(uint64_t j, uint64_t g) const {
+        const Rec& r = recs[j % (NCTL - 1)];
+        return st->seg[j % NSEG] + STREAM_BACK + (g - r.tb * (uint64_t)TB);
+    }
+};
+
+static int pass_host(ntg_ctx* ctx, const uint8_t* bytes, uint64_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec,
+                     PassResult* out) {
+    SegmentFeed f;
+    NTG_TRY(f.open(ctx, format, cfg, tile_bytes, spec));
+    *out = PassResult{};
+    auto check = [&](uint64_t, const LaunchCtl& c) { out->add(c); return (int)NTG_OK; };
+    const uint64_t seg_bytes = f.seg_tiles() * (uint64_t)tile_bytes;
+    uint64_t off = 0;
+    for (;;) {
+        const bool final = n - off <= seg_bytes;
+        const size_t len = (size_t)(final ? n - off : seg_bytes);
+        NTG_TRY(f.submit(bytes + off, len, final, n, check));
+        off += len;
+        if (final) break;
+    }
+    return f.drain(check);
+}
+
+// forward: exact record-table path (windowed)
+struct ByteSource { const uint8_t* host; const uint8_t* dev; uint64_t n; bool more_behind = false; };   // more_behind: the stream continues behind byte n
+static int exact_tally(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, PassResult* out, ntg_parse_error* err);
+
+static void tallies_from_pass(const PassResult& r, ntg_tallies* out) {
+    std::memset(out, 0, sizeof(*out));
+    out->n_records = r.tallies[0]; out->n_bases = r.tallies[1]; out->n_kmers = r.tallies[2]; out->n_not_rc = r.tallies[3];
+    out->kmer_sum_lo = r.tallies[4]; out->kmer_sum_hi = r.tallies[5]; out->n_query = r.tallies[6];
+    out->n_minimizers = r.tallies[7]; out->minimizer_sum = r.tallies[8];
+    for (int i = 0; i < 5; i++) out->reserved[2 + i] = r.tallies[9 + i];   // NTG_STATS builds: per-CTA cycle accounting
+    out->reserved[5] = r.tallies[14]; out->reserved[6] = r.tallies[15];
+}
+
+// The error of the record that starts at stream byte E (the kernel's first-error key), classified by the record scanner on a
+// window at E: kind, line, id exactly as the reference reports them.  `recs_before` = records delivered before it.
+static int classify_error_at(ntg_ctx* ctx, const ByteSource& src, uint64_t E, uint64_t recs_before, ntg_parse_error* err, bool* confirmed) {
+    *confirmed = false;
+    for (uint64_t W = uint64_t(1) << 20;; W <<= 4) {
+        const uint64_t len = src.n - E < W ? src.n - E : W;
+        const bool whole = E + len == src.n, at_eof = whole && !src.more_behind;
+        if (len >= 0xFFFFFFF0ull) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "a record larger than 4 GiB");
+        ntg_records* r = nullptr;
+        NTG_TRY(run_parse_device(ctx, src.host ? src.host + E : nullptr, src.dev ? src.dev + E : nullptr, (size_t)len, &r, nullptr, NTG_FMT_FASTQ, at_eof));
+        const bool found = r->error.kind != 0 && r->error.record_index == 0;
+        const bool cut = !at_eof && r->n_records == 0 && r->error.kind == 0;       // the window does not hold the whole record yet
+        if (found) {
+            if (err) { *err = r->error; err->line += 4 * recs_before; err->record_index += recs_before; }
+            *confirmed = true;
+        }
+        ntg_records_free(r);
+        if (!cut || whole) return NTG_OK;                            // (whole && cut: the source does not hold the whole record)
+    }
+}
+
+// Whole-input tallies with the reference's iterator semantics.  `run(n_eff, spec, &result)` makes one pass over the first
+// n_eff bytes of the source (resident or streamed); every pass can be repeated because the caller still holds the bytes.
+template <typename Run>
+static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, Run&& run, ntg_tallies* out, ntg_parse_error* err) {
+    if (err) { std::memset(err, 0, sizeof(*err)); err->format = format; }
+    PassResult r;
+    NTG_TRY(run(src.n, true, &r));
+    uint32_t spec_missed = 0;
+    if (r.flags & fused::FLAG_SPEC_MISS) { spec_missed = r.flags; NTG_TRY(run(src.n, false, &r)); }   // a speculated FASTQ line phase was wrong
+    if (r.flags == 0) { tallies_from_pass(r, out); out->reserved[1] = spec_missed; return NTG_OK; }
+    const uint32_t why = r.flags;
+    if (r.flags == fused::FLAG_PARSE_ERROR && format == NTG_FMT_FASTA) {
+        // only the end-of-stream rule can fail (fasta.rs:348-356): the last record is not delivered, nothing of it was tallied
+        tallies_from_pass(r, out);
+        if (err) { err->kind = (int32_t)r.fin[0]; err->line = r.fin[1]; err->record_index = r.fin[2]; }
+        out->reserved[1] = spec_missed;
+        return NTG_OK;
+    }
+    if (r.flags == fused::FLAG_PARSE_ERROR && r.err_key != ~0ull) {
+        // replay the stream truncated at the first failing record, then classify the failure there
+        const uint64_t E = r.err_key >> 2;
+        PassResult t;
+        if (E >= 2) {
+            NTG_TRY(run(E, true, &t));
+            if (t.flags & fused::FLAG_SPEC_MISS) NTG_TRY(run(E, false, &t));
+        }
+        if (t.flags == 0) {
+            bool confirmed = false;
+            ntg_parse_error e2; std::memset(&e2, 0, sizeof(e2)); e2.format = format;
+            NTG_TRY(classify_error_at(ctx, src, E, t.tallies[0], &e2, &confirmed));
+            if (confirmed) {
+                tallies_from_pass(t, out);
+                if (err) *err = e2;
+                out->reserved[1] = spec_missed;
+                return NTG_OK;
+            }
+        }
+    }
+    // ---- exact path: record table on the device window by window, one thread per delivered record
+    PassResult x;
+    NTG_TRY(exact_tally(ctx, src, format, cfg, &x, err));
+    tallies_from_pass(x, out);
+    out->reserved[1] = spec_missed;
+    out->reserved[0] = why;                 // why the exact path ran: 1 parse error, 2 newline-dense tile, 4 whitespace run > halo
+    return NTG_OK;
+}
+
+static int exact_tally(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, PassResult* out, ntg_parse_error* err) {
+    FusedState* st = ctx->fused;
+    *out = PassResult{};
+    if (err) { std::memset(err, 0, sizeof(*err)); err->format = format; }
+    LaunchCtl* c = st->ctl + CTL_REDO;
+    NTG_CUDA(ctx, cudaMemsetAsync(c, 0, sizeof(LaunchCtl), ctx->stream));
+    fused::Params P{};
+    P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0;
+    if (cfg->has_query)
+        for (uint32_t i = 0; i < cfg->k; i++) { P.q_hi = (P.q_hi << 2) | (P.q_lo >> 62); P.q_lo = (P.q_lo << 2) | host_luts().code[cfg->query[i]]; }
+    P.tallies = c->tallies; P.flags = &c->flags;
+    uint64_t pos = 0, rec_base = 0, line_base = 0;
+    uint64_t W = uint64_t(1) << 30;                                   // window (the record scanner indexes with 32 bits)
+    bool stop = false;
+    while (pos < src.n && !stop) {
+        const uint64_t len = src.n - pos < W ? src.n - pos : W;
+        const bool at_eof = pos + len == src.n;
+        ntg_records* recs = nullptr;
+        DevBuf<ntg_record> drecs; DevBuf<uint8_t> dwin;
+        uint64_t consumed = 0;
+        NTG_TRY(run_parse_device(ctx, src.host ? src.host + pos : nullptr, src.dev ? src.dev + pos : nullptr, (size_t)len, &recs, &drecs, format, at_eof,
+                                 &consumed, &dwin));
+        if (recs->n_records) {
+            P.bytes = src.dev ? src.dev + pos : dwin.p;
+            unsigned grid = (unsigned)((recs->n_records + 127) / 128);
+            if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
+            if (P.k > 32) fused::k_tally_records<2, false><<<grid, 128, 0, ctx->stream>>>(P, drecs.p, recs->n_records);
+            else if (P.m == 0) fused::k_tally_records<1, false><<<grid, 128, 0, ctx->stream>>>(P, drecs.p, recs->n_records);
+            else fused::k_tally_records<1, true><<<grid, 128, 0, ctx->stream>>>(P, drecs.p, recs->n_records);
+            ctx->launches++;
+            cudaError_t e = cudaGetLastError();
+            if (!e) e = cudaStreamSynchronize(ctx->stream);           // (the window buffers are freed at the end of this iteration)
+            if (e) { ntg_records_free(recs); return ntg_set_error(ctx, NTG_ECUDA, "exact path: %s", cudaGetErrorString(e)); }
+        }
+        if (recs->error.kind) {
+            if (err) { *err = recs->error; err->record_index += rec_base; err->line += line_base; }
+            stop = true;
+        } else if (!at_eof) {
+            if (consumed == 0) {                                       // not even one complete record in the window: widen it
+                ntg_records_free(recs);
+                if (W >= 0xF0000000ull) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "a record larger than 3.75 GiB");
+                W = W * 2 < 0xF0000000ull ? W * 2 : 0xF0000000ull;
+                continue;
+            }
+            line_base += recs->final_line - 1;
+        }
+        rec_base += recs->n_records;
+        pos = at_eof ? src.n : pos + consumed;
+        ntg_records_free(recs);
+    }
+    NTG_CUDA(ctx, cudaMemcpyAsync(st->h_ctl + CTL_REDO, c, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->add(st->h_ctl[CTL_REDO]);
+    out->flags = 0;
     return NTG_OK;
 }
 

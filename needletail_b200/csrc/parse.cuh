@@ -132,8 +132,14 @@ static void host_error_id(const Peek& pk, uint64_t start, uint64_t seq, ntg_pars
     }
 }
 
+// One window of a stream.  `force_format` = 0: sniff (the window is the start of the stream), else the format of the stream
+// this window continues.  `at_eof` = false: the stream continues behind the window - only records that are complete inside
+// it are delivered (FASTQ: four newlines; FASTA: followed by another record start), no end-of-stream rule runs, and
+// *consumed = offset of the first byte not covered by a delivered record (where the next window must start).  Offsets and
+// line numbers are relative to the window.  keep_drecs / keep_dbytes: the caller takes over the device copies.
 static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* dev_in, size_t n, ntg_records** out,
-                            DevBuf<ntg_record>* keep_drecs) {
+                            DevBuf<ntg_record>* keep_drecs, int force_format = 0, bool at_eof = true, uint64_t* consumed = nullptr,
+                            DevBuf<uint8_t>* keep_dbytes = nullptr) {
     using namespace parse;
     if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
     *out = nullptr;
@@ -146,17 +152,24 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
     res->_priv = priv;
     auto done = [&](int st) { if (st != NTG_OK) { delete priv; delete res; } else *out = res; return st; };
 
-    // sniff: parse_fastx_reader / get_fastx_reader (parser/mod.rs:85-93,37-46)
-    if (n < 2) { res->error.kind = NTG_EEMPTY_FILE; return done(NTG_OK); }
-    const uint8_t b0 = pk.at(0);
-    if (b0 == '>') res->format = NTG_FMT_FASTA;
-    else if (b0 == '@') res->format = NTG_FMT_FASTQ;
-    else { res->error.kind = NTG_EUNKNOWN_FORMAT; return done(NTG_OK); }
+    if (consumed) *consumed = 0;
+    if (force_format) {
+        res->format = force_format;
+        if (n == 0) return done(NTG_OK);
+    } else {
+        // sniff: parse_fastx_reader / get_fastx_reader (parser/mod.rs:85-93,37-46)
+        if (n < 2) { res->error.kind = NTG_EEMPTY_FILE; return done(NTG_OK); }
+        const uint8_t b0 = pk.at(0);
+        if (b0 == '>') res->format = NTG_FMT_FASTA;
+        else if (b0 == '@') res->format = NTG_FMT_FASTQ;
+        else { res->error.kind = NTG_EUNKNOWN_FORMAT; return done(NTG_OK); }
+    }
     res->error.format = res->format;
     const bool fasta = res->format == NTG_FMT_FASTA;
     const uint32_t n32 = (uint32_t)n;
 
-    DevBuf<uint8_t> dbytes_own, f_nl, f_cr, f_st;
+    DevBuf<uint8_t> dbytes_local, f_nl, f_cr, f_st;
+    DevBuf<uint8_t>& dbytes_own = keep_dbytes ? *keep_dbytes : dbytes_local;
     DevBuf<uint32_t> nlidx, cridx, stidx, tmp, nlpos, stpos;
     struct { const uint8_t* p; } dbytes{dev_in};
     if (!dev_in) {
@@ -219,6 +232,8 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
             res->error.kind = ek; res->error.record_index = ferr;
             res->error.line = 1 + 4ull * ferr + (ek == NTG_EINVALID_SEPARATOR ? 2 : 0);     // fastq.rs:246,256,281
             if (ek != NTG_EINVALID_START) host_error_id(pk, bad.start, bad.seq_b, &res->error);
+        } else if (!at_eof) {
+            if (consumed) *consumed = n_complete ? (uint64_t)tailnl[0] + 1 : 0;
         } else {
             // end of stream: check_end (fastq.rs:337-356)
             uint64_t start = n_complete ? (uint64_t)tailnl[0] + 1 : 0;
@@ -284,7 +299,13 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         if (priv->recs.alloc(n_st)) return done(ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed"));
         PCUDA(cudaMemcpy(priv->recs.p, drecs.p, (size_t)n_st * sizeof(ntg_record), cudaMemcpyDeviceToHost));
         res->n_records = total; res->records = priv->recs.p;
-        if (bad) {
+        if (!at_eof) {
+            // the last record start of the window is not delivered: the record may continue behind the window
+            const ntg_record& l = priv->recs.p[n_st - 1];
+            res->n_records = n_st - 1;
+            res->final_line = l.line; res->final_byte = l.start;
+            if (consumed) *consumed = l.start;
+        } else if (bad) {
             const ntg_record& b = priv->recs.p[n_st - 1];
             res->error.kind = NTG_EUNEXPECTED_END; res->error.record_index = n_st - 1;
             res->error.line = b.line;                                   // fasta.rs:348-356

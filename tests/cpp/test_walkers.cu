@@ -172,8 +172,13 @@ static int test_first_lines_event(std::mt19937_64& rng) {
         uint32_t Cs = 0, nl4[4] = {0, 0, 0, 0};
         for (size_t g = g0; g < gnl.size() && gnl[g] < tile_start + avail; g++) { if (Cs < 4) nl4[Cs] = (uint32_t)(gnl[g] - tile_start); Cs++; }
         const bool line0 = tile_start == 0 || bytes[tile_start - 1] == '\n';
-        Acc got; uint32_t slow = 0;
-        for (uint32_t i = 0; i < 4 && i <= Cs; i++) fused::first_lines_event(bytes, tile_start, nl4, Cs, avail, line0, pre, i, got, slow);
+        Acc got; uint32_t slow = 0; unsigned long long got_key = ~0ull, want_key = ~0ull;
+        for (uint32_t i = 0; i < 4 && i <= Cs; i++) fused::first_lines_event(bytes, 0, tile_start, nl4, Cs, avail, line0, pre, i, got, slow, &got_key);
+        auto want_note = [&](size_t g, uint32_t role, uint32_t check) {         // the record of line g starts at line g - role
+            const size_t g0r = g - role;
+            const uint64_t rs = g0r ? gnl[g0r - 1] + 1 : 0;
+            want_key = std::min<unsigned long long>(want_key, (rs << 2) | check);
+        };
         // the definition, on global line ordinals
         uint64_t want_bases = 0, want_rec = 0; bool want_err = false;
         auto line_len = [&](uint64_t ls, uint64_t q) { return (q - ls) - ((q > ls && bytes[q - 1] == '\r') ? 1 : 0); };
@@ -182,15 +187,16 @@ static int test_first_lines_event(std::mt19937_64& rng) {
             const uint32_t role = (uint32_t)(g & 3);
             const uint64_t ls = g ? gnl[g - 1] + 1 : 0;                        // global start of the line
             const bool starts_in_tile = ls >= tile_start && ls - tile_start < avail;
-            if (starts_in_tile && ((role == 0 && bytes[ls] != '@') || (role == 2 && bytes[ls] != '+'))) want_err = true;
+            if (starts_in_tile && role == 0 && bytes[ls] != '@') { want_err = true; want_note(g, 0, 0); }
+            if (starts_in_tile && role == 2 && bytes[ls] != '+') { want_err = true; want_note(g, 2, 1); }
             if (i < Cs) {
                 const uint64_t q = gnl[g];
                 if (role == 1) want_bases += line_len(ls, q);
                 else if (role == 3) {
-                    if (g < 3) want_err = true;
+                    if (g < 3) { want_err = true; want_key = 0; }
                     else {
                         const uint64_t q0 = gnl[g - 3], q1 = gnl[g - 2], q2 = gnl[g - 1];
-                        if (line_len(q0 + 1, q1) != line_len(q2 + 1, q)) want_err = true;
+                        if (line_len(q0 + 1, q1) != line_len(q2 + 1, q)) { want_err = true; want_note(g, 3, 2); }
                         want_rec++;
                     }
                 }
@@ -198,9 +204,10 @@ static int test_first_lines_event(std::mt19937_64& rng) {
         }
         const bool got_err = (slow & fused::FLAG_PARSE_ERROR) != 0;
         n_err += want_err; n_rec += (long)want_rec;
-        if (got.n_bases != want_bases || got.n_records != want_rec || got_err != want_err) {
-            std::printf("first_lines_event: tile [%llu,+%u) Cs %u: bases %llu/%llu records %llu/%llu err %d/%d\n", (unsigned long long)tile_start, avail, Cs,
-                        (unsigned long long)got.n_bases, (unsigned long long)want_bases, (unsigned long long)got.n_records, (unsigned long long)want_rec, got_err, want_err);
+        if (got.n_bases != want_bases || got.n_records != want_rec || got_err != want_err || got_key != want_key) {
+            std::printf("first_lines_event: tile [%llu,+%u) Cs %u: bases %llu/%llu records %llu/%llu err %d/%d key %llx/%llx\n", (unsigned long long)tile_start, avail, Cs,
+                        (unsigned long long)got.n_bases, (unsigned long long)want_bases, (unsigned long long)got.n_records, (unsigned long long)want_rec, got_err, want_err,
+                        got_key, want_key);
             fails++;
         }
     }

@@ -361,7 +361,8 @@ def test_fast_path_is_taken_on_clean_files(ctx):
     assert ctx.tally(fx["data/28S.fasta"], k=31, m=21)["fallback"] == 0
     assert ctx.tally(fx["data/PRJNA271013_head.fq"], k=31, m=21)["fallback"] == 0
     assert ctx.tally(fx["data/PRJNA271013_head.fq"][:-1], k=51)["fallback"] == 0
-    assert ctx.tally(fx["data/bad_header.fastq"], k=4)["fallback"] & 1            # parse error -> exact path
+    t = ctx.tally(fx["data/bad_header.fastq"], k=4)                                # parse error -> truncated replay, not the exact path
+    assert t["fallback"] == 0 and t["err_kind"] is not None
     assert ctx.tally(b">a\n" + b"A\n" * 60000, k=4)["fallback"] & 2               # newline-dense tile
 
 

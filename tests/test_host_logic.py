@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libntgpu.so does not export {n}"
     assert sorted(lib._declared) == names          # the ctypes face covers the whole header
-    assert lib.ntg_abi_version() == 2
+    assert lib.ntg_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

@@ -19,7 +19,7 @@ declare -A V=(
   [dc_ticket]="-DNTG_DC=1 -DNTG_TICKET=1"
   [dc_fp64min]="-DNTG_DC=1 -DNTG_FP64_MIN=1"
 )
-F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC --expt-relaxed-constexpr -ldl"
+F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC --expt-relaxed-constexpr -ldl -lz"
 case "${1:-}" in
   build)
     for n in "${!V[@]}"; do /usr/local/cuda/bin/nvcc $F ${V[$n]} -o needletail_b200/libntgpu_$n.so needletail_b200/csrc/ntgpu.cu 2>/dev/null & done; wait

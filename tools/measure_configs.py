@@ -77,7 +77,7 @@ def main():
         if any(t["ws_cycles"].values()):          # NTG_STATS build: per-CTA cycle accounting (see fused.cuh)
             c = t["ws_cycles"]
             out[-1]["stats"] = {"cta_cycles_sum": c["claim"], "lookback_cycles": c["scan"], "lookbacks": c["lookback_retry"],
-                                "barrier_wait_cycles_t0": c["walker_wait"], "walk_cycles_t0": c["walker_work"]}
+                                "barrier_wait_cycles_t0": c["walker_wait"], "walk_cycles_t0": c["walker_work"], "n_query_slot": t["n_query"]}
         print(json.dumps(out[-1]), flush=True)
     ctx.close()
 
