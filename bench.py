@@ -434,7 +434,7 @@ def main():
     ap.add_argument("--reads", type=int, default=100_000_000)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--k", type=int, default=31)
-    ap.add_argument("--m", type=int, default=21)
+    ap.add_argument("--m", "--minimizer-len", dest="m", type=int, default=21)
     ap.add_argument("--e2e-host-gib", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -144,9 +144,10 @@ int ntg_strip_returns(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, s
 /* sequence::complement + Sequence::reverse_complement (src/sequence.rs:67-105,202-208);
  * same offsets in and out */
 int ntg_reverse_complement(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint8_t* out);
-/* QualitySequence::quality_mask (src/sequence.rs:280-297) */
-int ntg_quality_mask(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* quals, const uint64_t* offs, size_t n,
-                     uint8_t score, uint8_t* out);
+/* QualitySequence::quality_mask (src/sequence.rs:280-297).  qual_offs = the offsets of the quals batch: NTG_EINVAL unless they
+ * equal offs (the reference only masks records whose lengths were validated as equal); NULL = the caller vouches for that. */
+int ntg_quality_mask(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* quals, const uint64_t* offs, const uint64_t* qual_offs,
+                     size_t n, uint8_t score, uint8_t* out);
 
 typedef struct ntg_items {
     uint64_t n_seqs;
@@ -167,6 +168,9 @@ void ntg_items_free(ntg_items* it);
  * 2-bit pack (bases compared as raw bytes exactly like the reference; ties => was_rc = 1). */
 int ntg_canonical_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const uint64_t* offs, size_t n,
                         uint32_t k, ntg_items** out);
+/* Sequence::kmers / kmer::Kmers (src/sequence.rs:245-247, src/kmer.rs:13-41): every window of k bytes, whatever the bytes are.
+ * The item is the input slice seqs[pos..pos+k) itself: only item_offs and pos are filled (was_rc, val_lo, val_hi are NULL). */
+int ntg_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint32_t k, ntg_items** out);
 /* Sequence::bit_kmers / bitkmer::BitNuclKmer (+ canonical) (src/sequence.rs:250-252,
  * src/bitkmer.rs:26-143).  1 <= k <= 32.  ties => (kmer, false). */
 int ntg_bit_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint32_t k, int canonical,

@@ -121,7 +121,8 @@ def load_library():
         "ntg_normalize": ([vp, vp, vp, sz, C.c_int, vp, vp, vp], C.c_int),
         "ntg_strip_returns": ([vp, vp, vp, sz, vp, vp, vp], C.c_int),
         "ntg_reverse_complement": ([vp, vp, vp, sz, vp], C.c_int),
-        "ntg_quality_mask": ([vp, vp, vp, vp, sz, C.c_uint8, vp], C.c_int),
+        "ntg_quality_mask": ([vp, vp, vp, vp, vp, sz, C.c_uint8, vp], C.c_int),
+        "ntg_kmers": ([vp, vp, vp, sz, u32, P(P(_Items))], C.c_int),
         "ntg_items_free": ([P(_Items)], None),
         "ntg_canonical_kmers": ([vp, vp, vp, vp, sz, u32, P(P(_Items))], C.c_int),
         "ntg_bit_kmers": ([vp, vp, vp, sz, u32, C.c_int, P(P(_Items))], C.c_int),
@@ -176,7 +177,7 @@ class Items:
         self.item_offs = np.ctypeslib.as_array(it.item_offs, shape=(n + 1,)).copy()
         self.pos = np.ctypeslib.as_array(it.pos, shape=(ni,)).copy() if ni else np.zeros(0, np.uint32)
         self.was_rc = (np.ctypeslib.as_array(it.was_rc, shape=(ni,)).copy() if ni else np.zeros(0, np.uint8)) if it.was_rc else None
-        self.val_lo = np.ctypeslib.as_array(it.val_lo, shape=(ni,)).copy() if ni else np.zeros(0, np.uint64)
+        self.val_lo = (np.ctypeslib.as_array(it.val_lo, shape=(ni,)).copy() if ni else np.zeros(0, np.uint64)) if it.val_lo else None
         self.val_hi = (np.ctypeslib.as_array(it.val_hi, shape=(ni,)).copy() if ni else np.zeros(0, np.uint64)) if it.val_hi else None
 
     def of(self, i):
@@ -325,10 +326,12 @@ class Context:
         return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(seqs))]
 
     def quality_mask(self, seqs, quals, score):
+        if len(seqs) != len(quals):
+            raise ValueError("quality_mask: one quality string per sequence")
         cat, offs = _batch(seqs)
-        qcat, _ = _batch(quals)
+        qcat, qoffs = _batch(quals)
         out = np.empty(max(1, cat.size), dtype=np.uint8)
-        self._ck(self.lib.ntg_quality_mask(self.h, _ptr(cat), _ptr(qcat), offs.ctypes.data, len(seqs), score, out.ctypes.data))
+        self._ck(self.lib.ntg_quality_mask(self.h, _ptr(cat), _ptr(qcat), offs.ctypes.data, qoffs.ctypes.data, len(seqs), score, out.ctypes.data))
         return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(seqs))]
 
     def _items(self, fn, *args):
@@ -344,6 +347,12 @@ class Context:
         rc = _batch(rcs)[0] if rcs is not None else None
         return self._items(self.lib.ntg_canonical_kmers, _ptr(cat), _ptr(rc) if rc is not None else None,
                            offs.ctypes.data, len(seqs), k)
+
+    def kmers(self, seqs, k):
+        """Sequence::kmers: list (one entry per sequence) of the k-byte windows, as bytes — ntg_kmers gives the positions"""
+        cat, offs = _batch(seqs)
+        it = self._items(self.lib.ntg_kmers, _ptr(cat), offs.ctypes.data, len(seqs), k)
+        return [[bytes(seqs[i][int(p):int(p) + k]) for p in it.pos[it.of(i)]] for i in range(len(seqs))]
 
     def bit_kmers(self, seqs, k, canonical=False):
         cat, offs = _batch(seqs)

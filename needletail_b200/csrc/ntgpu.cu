@@ -187,36 +187,49 @@ int ntg_strip_returns(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, s
     CTX_ENTER(ctx);
     return run_xform(ctx, seqs, offs, n, 2, out, out_offs, changed);
 }
-int ntg_reverse_complement(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint8_t* out) {
-    CTX_ENTER(ctx);
+// same-offset byte maps (reverse_complement, quality_mask) over runs of whole sequences
+static int run_bytemap(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* quals, const uint64_t* offs, size_t n, int score, uint8_t* out) {
     if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
-    BatchOnDevice b;
-    NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
-    if (!b.total) return NTG_OK;
-    DevBuf<uint8_t> dout;
-    if (dout.alloc(b.total)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
-    seqops::k_revcomp<<<seqops::grid_for(b.total), seqops::BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, dout.p);
-    ctx->launches++;
-    NTG_CUDA(ctx, cudaGetLastError());
-    NTG_CUDA(ctx, cudaMemcpyAsync(out, dout.p, b.total, cudaMemcpyDeviceToHost, ctx->stream));
-    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NTG_TRY(check_batch(ctx, seqs, offs, n));
+    std::vector<uint64_t> sub;
+    for (size_t a = 0; a < n;) {
+        const size_t e = next_run(offs, n, a);
+        sub.resize(e - a + 1);
+        for (size_t i = a; i <= e; i++) sub[i - a] = offs[i] - offs[a];
+        BatchOnDevice b;
+        NTG_TRY(upload_batch(ctx, seqs + offs[a], sub.data(), e - a, b));
+        if (b.total) {
+            DevBuf<uint8_t> dq, dout;
+            if (dout.alloc(b.total) || (quals && dq.alloc(b.total))) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+            if (quals) {
+                NTG_CUDA(ctx, cudaMemcpyAsync(dq.p, quals + offs[a], b.total, cudaMemcpyHostToDevice, ctx->stream));
+                seqops::k_qmask<<<seqops::grid_for(b.total), seqops::BLOCK, 0, ctx->stream>>>(b.seqs.p, dq.p, b.total, (uint8_t)score, dout.p);
+            } else {
+                seqops::k_revcomp<<<seqops::grid_for(b.total), seqops::BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, dout.p);
+            }
+            ctx->launches++;
+            NTG_CUDA(ctx, cudaGetLastError());
+            NTG_CUDA(ctx, cudaMemcpyAsync(out + offs[a], dout.p, b.total, cudaMemcpyDeviceToHost, ctx->stream));
+            NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        a = e;
+    }
     return NTG_OK;
 }
-int ntg_quality_mask(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* quals, const uint64_t* offs, size_t n, uint8_t score, uint8_t* out) {
+int ntg_reverse_complement(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint8_t* out) {
     CTX_ENTER(ctx);
-    if (!out || !quals) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
-    BatchOnDevice b;
-    NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
-    if (!b.total) return NTG_OK;
-    DevBuf<uint8_t> dq, dout;
-    if (dq.alloc(b.total) || dout.alloc(b.total)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
-    NTG_CUDA(ctx, cudaMemcpyAsync(dq.p, quals, b.total, cudaMemcpyHostToDevice, ctx->stream));
-    seqops::k_qmask<<<seqops::grid_for(b.total), seqops::BLOCK, 0, ctx->stream>>>(b.seqs.p, dq.p, b.total, score, dout.p);
-    ctx->launches++;
-    NTG_CUDA(ctx, cudaGetLastError());
-    NTG_CUDA(ctx, cudaMemcpyAsync(out, dout.p, b.total, cudaMemcpyDeviceToHost, ctx->stream));
-    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return NTG_OK;
+    return run_bytemap(ctx, seqs, nullptr, offs, n, 0, out);
+}
+int ntg_quality_mask(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* quals, const uint64_t* offs, const uint64_t* qual_offs, size_t n,
+                     uint8_t score, uint8_t* out) {
+    CTX_ENTER(ctx);
+    if (!quals && offs && n && offs[n]) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
+    // the reference masks records whose two lengths were validated as equal (fastq.rs:262-283): the batch must say so too
+    if (qual_offs)
+        for (size_t i = 0; i <= n; i++)
+            if (qual_offs[i] != offs[i]) return ntg_set_error(ctx, NTG_EINVAL, "sequence %zu: sequence and quality lengths differ", i ? i - 1 : 0);
+    static const uint8_t none = 0;
+    return run_bytemap(ctx, seqs, quals ? quals : &none, offs, n, score, out);
 }
 void ntg_items_free(ntg_items* it) {
     if (!it) return;
@@ -226,6 +239,10 @@ void ntg_items_free(ntg_items* it) {
 int ntg_canonical_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const uint64_t* offs, size_t n, uint32_t k, ntg_items** out) {
     CTX_ENTER(ctx);
     return run_kmers(ctx, seqs, rc, offs, n, k, 0, 0, out);
+}
+int ntg_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint32_t k, ntg_items** out) {
+    CTX_ENTER(ctx);
+    return run_kmers(ctx, seqs, nullptr, offs, n, k, 0, 4, out);
 }
 int ntg_bit_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, uint32_t k, int canonical, ntg_items** out) {
     CTX_ENTER(ctx);

@@ -22,25 +22,30 @@ __device__ __forceinline__ uint32_t seq_of(const uint32_t* __restrict__ offs, ui
 // ---- normalize / strip_returns: flag + changed, then scatter ---------------------------------
 // mode 0/1: sequence::normalize(iupac = mode)  (src/sequence.rs:19-62)
 // mode 2  : Sequence::strip_returns            (src/sequence.rs:165-191)
-__device__ __forceinline__ uint8_t xform(uint8_t b, int mode) {
-    if (mode == 2) return (b == '\r' || b == '\n') ? 0 : b;
-    return __ldg(&c_norm[mode][b]);
+// returns the output byte; *keep = false when the byte is deleted (mode 2 deletes only \r and \n: a NUL byte is kept)
+__device__ __forceinline__ uint8_t xform(uint8_t b, int mode, bool* keep) {
+    if (mode == 2) { *keep = !(b == '\r' || b == '\n'); return b; }
+    const uint8_t o = __ldg(&c_norm[mode][b]);
+    *keep = o != 0;
+    return o;
 }
 __global__ void __launch_bounds__(BLOCK) k_xform_flags(const uint8_t* __restrict__ seqs, const uint32_t* __restrict__ offs,
                                                        uint32_t nseq, uint32_t total, int mode,
                                                        uint8_t* __restrict__ keep, uint8_t* __restrict__ changed) {
     uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
     if (g >= total) return;
-    uint8_t b = seqs[g], o = xform(b, mode);
-    keep[g] = o != 0;
-    if (o != b) changed[seq_of(offs, nseq, g)] = 1;   // benign race: everyone writes 1
+    bool kp;
+    uint8_t b = seqs[g], o = xform(b, mode, &kp);
+    keep[g] = kp;
+    if (!kp || o != b) changed[seq_of(offs, nseq, g)] = 1;   // benign race: everyone writes 1
 }
 __global__ void __launch_bounds__(BLOCK) k_xform_scatter(const uint8_t* __restrict__ seqs, uint32_t total, int mode,
                                                          const uint32_t* __restrict__ idx, uint8_t* __restrict__ out) {
     uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
     if (g >= total) return;
-    uint8_t o = xform(seqs[g], mode);
-    if (o) out[idx[g]] = o;
+    bool kp;
+    uint8_t o = xform(seqs[g], mode, &kp);
+    if (kp) out[idx[g]] = o;
 }
 __global__ void __launch_bounds__(BLOCK) k_gather_offsets(const uint32_t* __restrict__ offs, uint32_t nseq,
                                                           const uint32_t* __restrict__ idx, uint64_t* __restrict__ out_offs) {
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(BLOCK) k_qmask(const uint8_t* __restrict__ seq
 // (the set of windows both CanonicalKmers, src/kmer.rs:84-129, and BitNuclKmer,
 //  src/bitkmer.rs:39-109, emit: every start whose k bytes are all in ACGTacgt)
 __global__ void __launch_bounds__(BLOCK) k_kmer_valid(const uint8_t* __restrict__ seqs, const uint32_t* __restrict__ offs,
-                                                      uint32_t nseq, uint32_t total, uint32_t k, uint8_t* __restrict__ valid) {
+                                                      uint32_t nseq, uint32_t total, uint32_t k, int any_base, uint8_t* __restrict__ valid) {
     uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
     if (g >= total) return;
     uint32_t s = seq_of(offs, nseq, g);
@@ -75,8 +80,9 @@ __global__ void __launch_bounds__(BLOCK) k_kmer_valid(const uint8_t* __restrict_
     uint8_t v = 0;
     if (g + k <= e) {
         v = 1;
-        for (uint32_t i = 0; i < k; i++)
-            if (__ldg(&c_code[seqs[g + i]]) > 3) { v = 0; break; }
+        if (!any_base)
+            for (uint32_t i = 0; i < k; i++)
+                if (__ldg(&c_code[seqs[g + i]]) > 3) { v = 0; break; }
     }
     valid[g] = v;
 }
@@ -84,6 +90,7 @@ __global__ void __launch_bounds__(BLOCK) k_kmer_valid(const uint8_t* __restrict_
 // mode 0: canonical_kmers (byte compare, ties -> rc, was_rc = 1; val = 2-bit pack of the chosen slice, k <= 64)
 // mode 1: bit_kmers(canonical = false)   mode 2: bit_kmers(canonical = true)   (k <= 32; ties -> original)
 // mode 3: bit minimizers (m)             (k <= 32)
+// mode 4: kmer::Kmers — every window, whatever its bytes (src/kmer.rs:13-41): positions only, the item IS the input slice
 __global__ void __launch_bounds__(BLOCK) k_kmer_emit(const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ rcs,
                                                      const uint32_t* __restrict__ offs, uint32_t nseq, uint32_t total,
                                                      uint32_t k, uint32_t m, int mode,
@@ -97,6 +104,7 @@ __global__ void __launch_bounds__(BLOCK) k_kmer_emit(const uint8_t* __restrict__
     uint32_t p = g - b, len = e - b;
     uint32_t o = idx[g];
     pos[o] = p;
+    if (mode == 4) return;
     if (mode == 0) {
         // result = buffer[pos..pos+k]; rc_result = rc_buffer[len-pos-k .. len-pos]   (src/kmer.rs:121-123)
         uint32_t rbase = b + (len - p - k);
@@ -156,7 +164,7 @@ static int upload_batch(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs,
         if (offs[i + 1] < offs[i]) return ntg_set_error(ctx, NTG_EINVAL, "offsets must be ascending");
     uint64_t total = offs[n];
     if (total >= 0xFFFFFFF0ull || n >= 0xFFFFFFF0ull)
-        return ntg_set_error(ctx, NTG_EUNSUPPORTED, "batch of %llu bytes: split batches at 4 GiB", (unsigned long long)total);
+        return ntg_set_error(ctx, NTG_EUNSUPPORTED, "a single sequence of %llu bytes: sequences are limited to 4 GiB", (unsigned long long)total);
     b.nseq = (uint32_t)n; b.total = (uint32_t)total;
     if (b.seqs.alloc(total) != cudaSuccess || b.offs.alloc(n + 1) != cudaSuccess)
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
@@ -168,10 +176,45 @@ static int upload_batch(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs,
     return NTG_OK;
 }
 
+// Batches beyond the 32-bit indices of one device pass are cut into runs of whole sequences (at most SUB_BATCH bytes each).
+constexpr uint64_t SUB_BATCH = uint64_t(1) << 31;
+static int check_batch(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n) {
+    if (!offs || (n && !seqs && offs[n] > 0)) return ntg_set_error(ctx, NTG_EINVAL, "null batch pointer");
+    if (offs[0] != 0) return ntg_set_error(ctx, NTG_EINVAL, "offs[0] must be 0");
+    for (size_t i = 0; i < n; i++)
+        if (offs[i + 1] < offs[i]) return ntg_set_error(ctx, NTG_EINVAL, "offsets must be ascending");
+    return NTG_OK;
+}
+// next run [a, b) of sequences starting at a: as many whole sequences as fit (at least one)
+static size_t next_run(const uint64_t* offs, size_t n, size_t a) {
+    size_t b = a + 1;
+    while (b < n && offs[b + 1] - offs[a] <= SUB_BATCH) b++;
+    return b;
+}
+
+static int run_xform_one(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, int mode,
+                         uint8_t* out, uint64_t* out_offs, uint8_t* changed);
 static int run_xform(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, int mode,
                      uint8_t* out, uint64_t* out_offs, uint8_t* changed) {
-    using namespace seqops;
     if (!out || !out_offs || !changed) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
+    NTG_TRY(check_batch(ctx, seqs, offs, n));
+    if (offs[n] <= SUB_BATCH) return run_xform_one(ctx, seqs, offs, n, mode, out, out_offs, changed);
+    uint64_t out_total = 0;
+    std::vector<uint64_t> sub, sub_out;
+    for (size_t a = 0; a < n;) {
+        const size_t b = next_run(offs, n, a);
+        sub.resize(b - a + 1); sub_out.resize(b - a + 1);
+        for (size_t i = a; i <= b; i++) sub[i - a] = offs[i] - offs[a];
+        NTG_TRY(run_xform_one(ctx, seqs + offs[a], sub.data(), b - a, mode, out + out_total, sub_out.data(), changed + a));
+        for (size_t i = a; i <= b; i++) out_offs[i] = out_total + sub_out[i - a];
+        out_total += sub_out[b - a];
+        a = b;
+    }
+    return NTG_OK;
+}
+static int run_xform_one(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs, size_t n, int mode,
+                         uint8_t* out, uint64_t* out_offs, uint8_t* changed) {
+    using namespace seqops;
     BatchOnDevice b;
     NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
     DevBuf<uint8_t> keep, dout, dchg; DevBuf<uint32_t> idx, tmp; DevBuf<uint64_t> dooffs;
@@ -205,15 +248,16 @@ struct ItemsPriv {
     PinBuf<uint8_t> was_rc;
 };
 
-// mode: 0 canonical_kmers, 1 bit_kmers, 2 bit_kmers canonical, 3 minimizers
-static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const uint64_t* offs, size_t n,
+// mode: 0 canonical_kmers, 1 bit_kmers, 2 bit_kmers canonical, 3 minimizers, 4 plain windows (Kmers)
+static int run_kmers_one(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const uint64_t* offs, size_t n,
                      uint32_t k, uint32_t m, int mode, ntg_items** out) {
     using namespace seqops;
     if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
     *out = nullptr;
     if (k == 0) return ntg_set_error(ctx, NTG_EINVAL, "k must be >= 1 (k = 0 panics in the reference, src/kmer.rs:91)");
     if (mode == 0 && k > 64) return ntg_set_error(ctx, NTG_EINVAL, "canonical_kmers: k <= 64 supported");
-    if (mode != 0 && k > 32) return ntg_set_error(ctx, NTG_EINVAL, "bit k-mers hold at most 32 bases (u64, src/bitkmer.rs:2-3)");
+    if (mode == 4 && k > 255) return ntg_set_error(ctx, NTG_EINVAL, "k is a u8 in the reference (src/kmer.rs:14)");
+    if (mode != 0 && mode != 4 && k > 32) return ntg_set_error(ctx, NTG_EINVAL, "bit k-mers hold at most 32 bases (u64, src/bitkmer.rs:2-3)");
     if (mode == 3 && (m == 0 || m > k)) return ntg_set_error(ctx, NTG_EINVAL, "minimizer needs 1 <= m <= k");
     BatchOnDevice b;
     NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
@@ -225,7 +269,7 @@ static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const
     if (valid.alloc(b.total) || idx.alloc((size_t)b.total + 1) || tmp.alloc(scan_tmp_count(b.total)) || dioffs.alloc(n + 1))
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     if (b.total) {
-        k_kmer_valid<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, k, valid.p);
+        k_kmer_valid<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, k, mode == 4 ? 1 : 0, valid.p);
         ctx->launches++;
     }
     NTG_TRY(exclusive_scan_u8(ctx, valid.p, idx.p, b.total, tmp.p));
@@ -234,8 +278,9 @@ static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const
     uint32_t n_items = 0;
     NTG_CUDA(ctx, cudaMemcpyAsync(&n_items, idx.p + b.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    bool want_hi = (mode == 0 && k > 32), want_rc = (mode != 3);
-    if (dpos.alloc(n_items) || dlo.alloc(n_items) || (want_hi && dhi.alloc(n_items)) || dwas.alloc(n_items))
+    const bool want_val = mode != 4;
+    bool want_hi = (mode == 0 && k > 32), want_rc = (mode != 3 && mode != 4);
+    if (dpos.alloc(n_items) || (want_val && dlo.alloc(n_items)) || (want_hi && dhi.alloc(n_items)) || dwas.alloc(n_items))
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     if (b.total && n_items) {
         k_kmer_emit<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, rc ? drc.p : nullptr, b.offs.p, b.nseq, b.total, k, m,
@@ -246,13 +291,13 @@ static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const
     auto* priv = new ItemsPriv();
     auto* it = new ntg_items();
     auto fail = [&](int st, const char* msg) { delete priv; delete it; return ntg_set_error(ctx, st, "%s", msg); };
-    if (priv->item_offs.alloc(n + 1) || priv->pos.alloc(n_items) || priv->val_lo.alloc(n_items) ||
+    if (priv->item_offs.alloc(n + 1) || priv->pos.alloc(n_items) || (want_val && priv->val_lo.alloc(n_items)) ||
         (want_hi && priv->val_hi.alloc(n_items)) || (want_rc && priv->was_rc.alloc(n_items)))
         return fail(NTG_ENOMEM, "pinned allocation failed");
     cudaError_t e = cudaMemcpyAsync(priv->item_offs.p, dioffs.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (!e && n_items) {
         e = cudaMemcpyAsync(priv->pos.p, dpos.p, (size_t)n_items * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (!e) e = cudaMemcpyAsync(priv->val_lo.p, dlo.p, (size_t)n_items * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!e && want_val) e = cudaMemcpyAsync(priv->val_lo.p, dlo.p, (size_t)n_items * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (!e && want_hi) e = cudaMemcpyAsync(priv->val_hi.p, dhi.p, (size_t)n_items * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (!e && want_rc) e = cudaMemcpyAsync(priv->was_rc.p, dwas.p, (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream);
     }
@@ -261,7 +306,55 @@ static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const
     it->n_seqs = n; it->n_items = n_items;
     it->item_offs = priv->item_offs.p; it->pos = priv->pos.p;
     it->was_rc = want_rc ? priv->was_rc.p : nullptr;
-    it->val_lo = priv->val_lo.p; it->val_hi = want_hi ? priv->val_hi.p : nullptr;
+    it->val_lo = want_val ? priv->val_lo.p : nullptr; it->val_hi = want_hi ? priv->val_hi.p : nullptr;
+    it->_priv = priv;
+    *out = it;
+    return NTG_OK;
+}
+
+static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const uint64_t* offs, size_t n,
+                     uint32_t k, uint32_t m, int mode, ntg_items** out) {
+    if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output pointer");
+    *out = nullptr;
+    NTG_TRY(check_batch(ctx, seqs, offs, n));
+    if (offs[n] <= SUB_BATCH) return run_kmers_one(ctx, seqs, rc, offs, n, k, m, mode, out);
+    // runs of whole sequences, merged into one result (item offsets shifted by the items of the runs before)
+    std::vector<ntg_items*> parts;
+    auto drop = [&]() { for (auto* p : parts) ntg_items_free(p); };
+    std::vector<uint64_t> sub;
+    uint64_t n_items = 0;
+    for (size_t a = 0; a < n;) {
+        const size_t b = next_run(offs, n, a);
+        sub.resize(b - a + 1);
+        for (size_t i = a; i <= b; i++) sub[i - a] = offs[i] - offs[a];
+        ntg_items* part = nullptr;
+        const int st = run_kmers_one(ctx, seqs + offs[a], rc ? rc + offs[a] : nullptr, sub.data(), b - a, k, m, mode, &part);
+        if (st != NTG_OK) { drop(); return st; }
+        parts.push_back(part); n_items += part->n_items;
+        a = b;
+    }
+    auto* priv = new ItemsPriv();
+    auto* it = new ntg_items();
+    const bool want_val = parts[0]->val_lo != nullptr, want_hi = parts[0]->val_hi != nullptr, want_rc = parts[0]->was_rc != nullptr;
+    if (priv->item_offs.alloc(n + 1) || priv->pos.alloc(n_items) || (want_val && priv->val_lo.alloc(n_items)) ||
+        (want_hi && priv->val_hi.alloc(n_items)) || (want_rc && priv->was_rc.alloc(n_items))) {
+        delete priv; delete it; drop();
+        return ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed");
+    }
+    uint64_t io = 0; size_t so = 0;
+    for (auto* p : parts) {
+        for (uint64_t i = 0; i <= p->n_seqs; i++) priv->item_offs.p[so + i] = io + p->item_offs[i];
+        std::memcpy(priv->pos.p + io, p->pos, p->n_items * sizeof(uint32_t));
+        if (want_val) std::memcpy(priv->val_lo.p + io, p->val_lo, p->n_items * sizeof(uint64_t));
+        if (want_hi) std::memcpy(priv->val_hi.p + io, p->val_hi, p->n_items * sizeof(uint64_t));
+        if (want_rc) std::memcpy(priv->was_rc.p + io, p->was_rc, p->n_items);
+        io += p->n_items; so += p->n_seqs;
+    }
+    drop();
+    it->n_seqs = n; it->n_items = n_items;
+    it->item_offs = priv->item_offs.p; it->pos = priv->pos.p;
+    it->was_rc = want_rc ? priv->was_rc.p : nullptr;
+    it->val_lo = want_val ? priv->val_lo.p : nullptr; it->val_hi = want_hi ? priv->val_hi.p : nullptr;
     it->_priv = priv;
     *out = it;
     return NTG_OK;

@@ -22,6 +22,29 @@ def pytest_sessionstart(session):
         nt_build.build()
 
 
+def _have_sm100_gpu():
+    try:
+        import ctypes as C
+        import needletail_b200 as nt
+        lib = nt.load_library()
+        h = C.c_void_p()
+        if lib.ntg_create(0, C.byref(h)) != 0:
+            return False
+        lib.ntg_destroy(h)
+        return True
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not errors) on a box without an sm_100 device (round-1 ADVICE)."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not _have_sm100_gpu():
+        skip = pytest.mark.skip(reason="no sm_100 CUDA device: run under gpurun")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 _FIXTURES = None
 
 

@@ -98,6 +98,33 @@ def test_strip_revcomp_qmask_gpu(ctx):
     assert ctx.quality_mask([b"AGCT"], [b"AAA0"], ord("5")) == [b"AGCN"]   # src/sequence.rs:370-374
 
 
+def test_kmers_windows_and_strip_nul_and_qmask_lengths(ctx):
+    import needletail_b200 as nt
+    # Sequence::kmers (src/kmer.rs:13-41, src/sequence.rs:245): every window, whatever the bytes
+    seqs = [b"ACGNT\nAC", b"", b"AC", b"ACG", b"xyz-!"]
+    for k in (1, 3, 5, 9):
+        got = ctx.kmers(seqs, k)
+        assert got == [[s[i:i + k] for i in range(max(0, len(s) - k + 1))] for s in seqs], k
+    with pytest.raises(nt.NtgError):
+        ctx.kmers(seqs, 0)
+    # strip_returns deletes \r and \n only: a NUL byte is data (round-1 ADVICE)
+    out, ch = ctx.strip_returns([b"AC\0GT\r\n", b"\0", b"ACGT"])
+    assert out == [b"AC\0GT", b"\0", b"ACGT"] and ch == [True, False, False]
+    # quality_mask: sequence and quality lengths must agree per record (sequence.rs:280-297 works on validated records)
+    assert ctx.quality_mask([b"ACGT", b"GG"], [b"I!I!", b"!I"], 34) == [b"ANGN", b"NG"]
+    with pytest.raises(nt.NtgError):
+        ctx.quality_mask([b"ACGT", b"GG"], [b"I!I", b"!I!"], 34)
+    with pytest.raises(ValueError):
+        ctx.quality_mask([b"ACGT"], [], 34)
+    rng = random.Random(17)
+    for _ in range(20):
+        n = rng.randrange(1, 40)
+        ss = [bytes(rng.choice(b"ACGTN") for _ in range(rng.randrange(0, 300))) for _ in range(n)]
+        qq = [bytes(rng.randrange(33, 75) for _ in range(len(s))) for s in ss]
+        sc = rng.randrange(33, 75)
+        assert ctx.quality_mask(ss, qq, sc) == [bytes(78 if q < sc else b for b, q in zip(s, qv)) for s, qv in zip(ss, qq)]
+
+
 def oracle_items_canonical(seqs, k, rcs=None):
     pos, fl, lo, hi, offs = [], [], [], [], [0]
     for i, s in enumerate(seqs):
