@@ -1210,7 +1210,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
 #if NTG_STATS
             st_mark = clock64();
 #endif
-            if (S.pend_valid) {
+            const bool had_pending = S.pend_valid != 0;
+            __syncwarp();                                       // (every lane has read the flag before lane 0 sets it again below)
+            if (had_pending) {
                 resolve_pending(P, S, epoch, lane, acc, slow);
 #if NTG_STATS
                 st_nlb++;
