@@ -255,6 +255,14 @@ int ntg_stream_commit(ntg_stream* s, size_t n);
 /* one more piece of a gzip stream (magic 1f 8b; src/parser/mod.rs:96-108): multi-member like flate2::MultiGzDecoder.
  * threads > 1 and a BGZF file (member sizes in the gzip extra field): members are inflated in parallel, in place. */
 int ntg_stream_feed_gz(ntg_stream* s, const uint8_t* gz, size_t n, int threads);
+/* threads == NTG_GZ_DEVICE (0) on a session that has been fed nothing else, and a BGZF file: the members are inflated ON THE
+ * DEVICE (one thread per member, RFC 1951 decoder in needletail_b200/csrc/inflate.cuh).  Only the compressed bytes cross PCIe;
+ * the text is written straight into the device segment the fused kernel reads and never exists on the host.  Lengths are
+ * checked against ISIZE, CRC-32 is not recomputed.  A non-BGZF gzip stream falls back to the sequential host inflate. */
+#define NTG_GZ_DEVICE 0
+/* the device-side DEFLATE decoder on its own: a whole BGZF blob, host to host.  *out_len = decompressed size (also when
+ * out_cap is too small: NTG_EINVAL then).  Corrupt members: NTG_EIO. */
+int ntg_inflate_bgzf(ntg_ctx* ctx, const uint8_t* gz, size_t n, uint8_t* out, size_t out_cap, size_t* out_len);
 int ntg_stream_finish(ntg_stream* s, ntg_tallies* out, ntg_parse_error* err);
 uint64_t ntg_stream_bytes(const ntg_stream* s);                              /* decompressed bytes fed so far */
 void ntg_stream_close(ntg_stream* s);

@@ -115,6 +115,7 @@ def load_library():
         "ntg_stream_commit": ([vp, sz], C.c_int),
         "ntg_stream_feed_gz": ([vp, vp, sz, C.c_int], C.c_int),
         "ntg_stream_finish": ([vp, P(_Tallies), P(_ParseError)], C.c_int),
+        "ntg_inflate_bgzf": ([vp, vp, sz, vp, sz, P(sz)], C.c_int),
         "ntg_stream_bytes": ([vp], u64),
         "ntg_stream_close": ([vp], None),
         "ntg_tally_fastx_file": ([vp, cp, P(_TallyConfig), C.c_int, P(_Tallies), P(_ParseError)], C.c_int),
@@ -428,6 +429,17 @@ class Context:
         cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
         self._ck(self.lib.ntg_tally_fastx_file(self.h, os.fsencode(path), C.byref(cfg), threads, C.byref(t), C.byref(e)))
         return self._tally_result(t, e)
+
+    def inflate_bgzf(self, blob):
+        """BGZF bytes -> text, inflated by the device-side DEFLATE decoder — ntg_inflate_bgzf"""
+        arr = _as_u8(blob)
+        n = C.c_size_t()
+        st = self.lib.ntg_inflate_bgzf(self.h, _ptr(arr), arr.size, None, 0, C.byref(n))
+        if st not in (OK, 16):
+            self._ck(st)
+        out = np.empty(max(1, n.value), dtype=np.uint8)
+        self._ck(self.lib.ntg_inflate_bgzf(self.h, _ptr(arr), arr.size, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].tobytes()
 
     def stream(self, k, m=0, iupac=False, query=None):
         """A tally session over a stream of unknown length (parse_fastx_reader<R: Read>) — ntg_stream_*"""

@@ -11,6 +11,8 @@
 // classifies the error with the record scanner on a window at E.  Inputs the single pass cannot take (newline-dense
 // tiles, whitespace runs longer than the halo) go to the exact record-table path, window by window.
 #pragma once
+#include <functional>
+
 #include "fused.cuh"
 #include "parse.cuh"
 
@@ -170,17 +172,21 @@ static uint32_t pick_tile_bytes(const uint8_t* sample, size_t ns, int format) {
 }
 
 // Start a pass: a fresh range of slot generations and the launch-invariant kernel parameters.
-static int fused_begin_pass(ntg_ctx* ctx, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool allow_spec, uint64_t max_tiles) {
+// max_tiles: upper bound of the pass's tile count (wrap check); tiles_now: tiles known so far (streamed passes update epoch_tiles as they go)
+static int fused_begin_pass(ntg_ctx* ctx, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool allow_spec, uint64_t max_tiles,
+                            uint64_t tiles_now) {
     NTG_TRY(fused_init(ctx));
     FusedState* st = ctx->fused;
-    // the previous pass used epoch .. epoch + (its tiles >> SLOT_SHIFT)
-    st->epoch = (st->epoch + 1 + (uint32_t)(st->epoch_tiles >> SLOT_SHIFT)) & 0x3FFFFFFFu;
-    if (st->epoch + (max_tiles >> SLOT_SHIFT) + 2 >= 0x3FFFFFFFull) {       // (once per 2^30 passes) start the generations over
+    // the previous pass used generations epoch .. epoch + (its tiles >> SLOT_SHIFT); this one may use up to max_tiles >> SLOT_SHIFT
+    // more.  Generations live in 30 bits: before they would wrap (and meet stale slots of old passes) the ring is cleared.
+    uint64_t next = (uint64_t)st->epoch + 1 + (st->epoch_tiles >> SLOT_SHIFT);
+    if (next + (max_tiles >> SLOT_SHIFT) + 2 >= 0x3FFFFFFFull) {
         NTG_CUDA(ctx, cudaMemsetAsync(st->slots, 0, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot), ctx->stream));
         NTG_CUDA(ctx, cudaMemsetAsync(st->cw, 0, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long), ctx->stream));
-        st->epoch = 1;
+        next = 1;
     }
-    st->epoch_tiles = max_tiles;
+    st->epoch = (uint32_t)next;
+    st->epoch_tiles = tiles_now;
     fused::Params& P = st->P;
     P = fused::Params{};
     P.slots = st->slots; P.cw = st->cw; P.slot_mask = (1u << SLOT_SHIFT) - 1; P.slot_shift = SLOT_SHIFT; P.final_state = st->final_state;
@@ -236,7 +242,7 @@ static int pass_resident(ntg_ctx* ctx, const uint8_t* dbytes, uint64_t n, int fo
                          PassResult* out) {
     FusedState* st = ctx->fused;
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
-    NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, num_tiles));
+    NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, num_tiles, num_tiles));
     NTG_TRY(fused_enqueue_launch(ctx, dbytes, 0, n, 0, num_tiles, true, 0));
     NTG_CUDA(ctx, cudaEventSynchronize(st->ev_done[0]));
     *out = PassResult{};
@@ -256,34 +262,42 @@ struct SegmentFeed {
     size_t prev_len = 0;
     uint64_t checked = 0;            // launches whose control block has been read back
     struct Rec { uint64_t tb, te, n_vis; size_t len; bool final; } recs[NCTL] = {};
+    size_t seg_target = STREAM_SEG;  // bytes of whole tiles per launch (device-side inflate uses larger segments)
 
-    int open(ntg_ctx* c, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec) {
+    int open(ntg_ctx* c, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec, size_t seg_bytes = STREAM_SEG) {
         ctx = c;
         NTG_TRY(fused_init(ctx));
         st = ctx->fused;
         TB = tile_bytes;
-        if (!st->seg[0]) {
-            st->seg_cap = STREAM_SEG + fused::TILE;
+        seg_target = seg_bytes;
+        if (st->seg_cap < seg_bytes + fused::TILE) {
+            NTG_CUDA(ctx, cudaDeviceSynchronize());
+            for (auto& p : st->seg) { cudaFree(p); p = nullptr; }
+            st->seg_cap = seg_bytes + fused::TILE;
             for (auto& p : st->seg)
-                if (cudaMalloc((void**)&p, STREAM_BACK + st->seg_cap) != cudaSuccess) { cudaGetLastError(); return ntg_set_error(ctx, NTG_ENOMEM, "device segment allocation failed"); }
+                if (cudaMalloc((void**)&p, STREAM_BACK + st->seg_cap) != cudaSuccess) { cudaGetLastError(); st->seg_cap = 0; return ntg_set_error(ctx, NTG_ENOMEM, "device segment allocation failed"); }
         }
-        NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, uint64_t(1) << 40));
+        NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, uint64_t(1) << 40, 0));
         // the copy stream must not overwrite the segments while kernels of an earlier call still read them
         NTG_CUDA(ctx, cudaEventRecord(st->ev_copy[0], ctx->stream));
         NTG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, st->ev_copy[0], 0));
         return NTG_OK;
     }
-    uint64_t seg_tiles() const { return STREAM_SEG / TB; }
+    uint64_t seg_tiles() const { return seg_target / TB; }
     // Submit the next `len` stream bytes (whole tiles unless final) from host memory.  Before buffer L % NSEG is reused
     // the launch that used it (L - NSEG) must have been checked: `check(j, ctl)` is called for every launch in order.
+    // `produce` (optional): instead of an H2D copy of `src`, the segment's bytes are produced on the device by work the
+    // callback enqueues on the copy stream: produce(data region of this segment, data region of the previous one, prev_len).
     template <typename Check>
-    int submit(const uint8_t* src, size_t len, bool final, uint64_t n_total, Check&& check) {
+    int submit(const uint8_t* src, size_t len, bool final, uint64_t n_total, Check&& check,
+               const std::function<int(uint8_t*, const uint8_t*, size_t)>* produce = nullptr) {
         if (len > st->seg_cap) return ntg_set_error(ctx, NTG_EINVAL, "segment larger than the device segment buffer");
         while (L >= (uint64_t)(NSEG - 1) && checked + (NSEG - 1) <= L) NTG_TRY(check_next(check));      // frees buffer L % NSEG
         const int b = (int)(L % NSEG), pb = (int)((L + NSEG - 1) % NSEG), ci = (int)(L % (NCTL - 1));
         uint8_t* buf = st->seg[b];
         if (L > 0) NTG_CUDA(ctx, cudaMemcpyAsync(buf, st->seg[pb] + prev_len, STREAM_BACK, cudaMemcpyDeviceToDevice, ctx->copy_stream));
-        if (len) NTG_CUDA(ctx, cudaMemcpyAsync(buf + STREAM_BACK, src, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (produce) NTG_TRY((*produce)(buf + STREAM_BACK, st->seg[pb] + STREAM_BACK, prev_len));
+        else if (len) NTG_CUDA(ctx, cudaMemcpyAsync(buf + STREAM_BACK, src, len, cudaMemcpyHostToDevice, ctx->copy_stream));
         NTG_CUDA(ctx, cudaEventRecord(st->ev_copy[b], ctx->copy_stream));
         NTG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->ev_copy[b], 0));
         const uint64_t tb = next_tile, start = tb * (uint64_t)TB;
@@ -294,6 +308,7 @@ struct SegmentFeed {
         NTG_TRY(fused_enqueue_launch(ctx, buf + STREAM_BACK - start, gmin, n_vis, tb, te, final, ci));
         recs[ci] = Rec{tb, te, n_vis, len, final};
         prev_len = len; next_tile = te; L++;
+        st->epoch_tiles = te;                                     // generations this pass has used so far
         return NTG_OK;
     }
     template <typename Check>

@@ -303,7 +303,7 @@ int ntg_tally_fastx_device_enqueue(ntg_ctx* ctx, uint64_t dptr, size_t n, const 
     int format; uint32_t tile_bytes;
     NTG_TRY(resident_sniff(ctx, dptr, n, true, &format, &tile_bytes));
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
-    NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, true, num_tiles));
+    NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, true, num_tiles, num_tiles));
     const bool reduce = (cfg->flags & NTG_TALLY_ALLREDUCE) != 0;
     if (reduce && !ctx->nccl_comm) return ntg_set_error(ctx, NTG_EINVAL, "NTG_TALLY_ALLREDUCE needs ntg_comm_init");
     NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
@@ -468,6 +468,48 @@ int ntg_tally_fastx_file(ntg_ctx* ctx, const char* path, const ntg_tally_config*
     }
     ntg_stream_close(s);
     return rc;
+}
+
+// GPU inflate of a whole BGZF blob, host to host (the device-side DEFLATE decoder on its own; the tally path uses it in-stream:
+// ntg_stream_feed_gz with threads == 0).
+int ntg_inflate_bgzf(ntg_ctx* ctx, const uint8_t* gz, size_t n, uint8_t* out, size_t out_cap, size_t* out_len) {
+    CTX_ENTER(ctx);
+    if ((n && !gz) || !out_len) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
+    *out_len = 0;
+    std::vector<gzdev::Member> members;
+    std::vector<uint8_t> payload;
+    uint64_t text = 0;
+    for (size_t off = 0; off < n;) {
+        const long ms = bgzf_member_size(gz + off, n - off);
+        if (ms == 0 && gz[off] == 0) break;                         // zero padding
+        if (ms <= 0 || (size_t)ms > n - off) return ntg_set_error(ctx, NTG_EIO, "not a complete BGZF member at offset %zu", off);
+        size_t po, pl;
+        if (!bgzf_payload(gz + off, (size_t)ms, &po, &pl)) return ntg_set_error(ctx, NTG_EIO, "truncated BGZF member at offset %zu", off);
+        const uint32_t isize = bgzf_isize(gz + off, (size_t)ms);
+        if (isize) {
+            members.push_back(gzdev::Member{payload.size(), text, (uint32_t)pl, isize});
+            payload.insert(payload.end(), gz + off + po, gz + off + po + pl);
+            text += isize;
+        }
+        off += (size_t)ms;
+    }
+    *out_len = (size_t)text;
+    if (text > out_cap) return ntg_set_error(ctx, NTG_EINVAL, "output buffer too small: %llu bytes needed", (unsigned long long)text);
+    if (members.empty()) return NTG_OK;
+    if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output");
+    NTG_TRY(inflate_init(ctx));
+    DevBuf<uint8_t> d_comp, d_out; DevBuf<gzdev::Member> d_mem; DevBuf<uint32_t> d_err;
+    if (d_comp.alloc(payload.size()) || d_out.alloc(text) || d_mem.alloc(members.size()) || d_err.alloc(1)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    NTG_CUDA(ctx, cudaMemcpyAsync(d_comp.p, payload.data(), payload.size(), cudaMemcpyHostToDevice, ctx->stream));
+    NTG_CUDA(ctx, cudaMemcpyAsync(d_mem.p, members.data(), members.size() * sizeof(gzdev::Member), cudaMemcpyHostToDevice, ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), ctx->stream));
+    NTG_TRY(inflate_enqueue(ctx, ctx->stream, d_comp.p, d_mem.p, (uint32_t)members.size(), d_out.p, d_err.p));
+    uint32_t e = 0;
+    NTG_CUDA(ctx, cudaMemcpyAsync(&e, d_err.p, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaMemcpyAsync(out, d_out.p, text, cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e) return ntg_set_error(ctx, NTG_EIO, "corrupt DEFLATE stream in member %u (code %u)", (e & 0x7FFFFFFFu) >> 5, e & 31u);
+    return NTG_OK;
 }
 
 // Chunked record scanner: one window of a stream (see run_parse_device in parse.cuh).

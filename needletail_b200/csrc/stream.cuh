@@ -19,6 +19,7 @@
 #include <thread>
 
 #include "fused_host.cuh"
+#include "inflate.cuh"
 
 constexpr int NPIN = 4;                                        // pinned staging buffers (launches L-3 .. L-1 stay readable while L fills)
 constexpr size_t ERRWIN_CAP = size_t(64) << 20;                // bytes kept behind a failing record for its classification
@@ -47,8 +48,10 @@ struct ntg_stream {
     bool in_submit = false;                                     // a check runs inside a submit: the staging buffer is not a launch yet
     std::string io_error;                                       // inflate failures (ParseErrorKind::Io)
     struct GzState* gz = nullptr;
+    struct DevGz* devgz = nullptr;                              // device-side inflate (BGZF): the text never exists on the host
 };
 static void gz_free(struct GzState* g);
+static void devgz_free(struct DevGz* d);
 
 static void stream_free(ntg_stream* s) {
     if (!s) return;
@@ -56,6 +59,7 @@ static void stream_free(ntg_stream* s) {
     if (s->opened && s->ctx && s->ctx->fused) cudaStreamSynchronize(s->ctx->stream);
     for (auto& p : s->pin) if (p) cudaFreeHost(p);
     gz_free(s->gz);
+    devgz_free(s->devgz);
     delete s;
 }
 
@@ -65,9 +69,13 @@ static int stream_create(ntg_ctx* ctx, const ntg_tally_config* cfg, ntg_stream**
     auto* s = new ntg_stream();
     s->ctx = ctx; s->cfg = *cfg;
     s->cap = STREAM_SEG + fused::TILE;
-    for (auto& p : s->pin)
-        if (cudaMallocHost((void**)&p, s->cap) != cudaSuccess) { cudaGetLastError(); stream_free(s); return ntg_set_error(ctx, NTG_ENOMEM, "pinned staging allocation failed"); }
     *out = s;
+    return NTG_OK;
+}
+static int stream_need_staging(ntg_stream* s) {                 // the pinned ring of text staging buffers, on first use
+    if (s->pin[0]) return NTG_OK;
+    for (auto& p : s->pin)
+        if (cudaMallocHost((void**)&p, s->cap) != cudaSuccess) { cudaGetLastError(); return ntg_set_error(s->ctx, NTG_ENOMEM, "pinned staging allocation failed"); }
     return NTG_OK;
 }
 
@@ -100,9 +108,16 @@ static void stream_collect_errwin(ntg_stream* s, uint64_t q) {
         const uint64_t b0 = r.tb * (uint64_t)s->TB;
         const uint64_t from = s->err_E > b0 ? s->err_E - b0 : 0;
         const size_t len = r.final ? (size_t)(r.n_vis - b0) : r.len;
-        if (from < len) append(s->pin[i % NPIN] + from, len - (size_t)from);
+        if (from >= len) continue;
+        if (!s->devgz) { append(s->pin[i % NPIN] + from, len - (size_t)from); continue; }
+        size_t n = len - (size_t)from;                          // device-side inflate: the text only exists in the device segments
+        if (s->errwin.size() + n > ERRWIN_CAP) { n = ERRWIN_CAP - s->errwin.size(); s->errwin_capped = true; }
+        const size_t old = s->errwin.size();
+        s->errwin.resize(old + n);
+        cudaMemcpy(s->errwin.data() + old, s->feed.device_addr(i, b0 + from), n, cudaMemcpyDeviceToHost);
     }
-    if (s->in_submit) append(s->pin[s->feed.L % NPIN], s->fill);
+    if (s->in_submit && !s->devgz) append(s->pin[s->feed.L % NPIN], s->fill);
+    if (s->devgz && !s->finished) s->errwin_capped = true;      // (text behind the resident launches is not available: treat as cut)
 }
 
 static int stream_check(ntg_stream* s, uint64_t j, const LaunchCtl& c_in) {
@@ -189,6 +204,8 @@ static int stream_submit_full(ntg_stream* s) {
 
 static int stream_acquire(ntg_stream* s, uint8_t** ptr, size_t* avail) {
     if (s->finished) return ntg_set_error(s->ctx, NTG_EINVAL, "stream already finished");
+    if (s->devgz) return ntg_set_error(s->ctx, NTG_EINVAL, "this session inflates on the device: feed it compressed bytes only");
+    NTG_TRY(stream_need_staging(s));
     if (s->fill == s->cap) NTG_TRY(stream_submit_full(s));
     *ptr = s->pin[s->feed.L % NPIN] + s->fill;
     *avail = s->cap - s->fill;
@@ -213,6 +230,7 @@ static int stream_feed(ntg_stream* s, const uint8_t* bytes, size_t n) {
 }
 
 static int gz_finish(ntg_stream* s);
+static int devgz_finish(ntg_stream* s);
 static int stream_finish(ntg_stream* s, ntg_tallies* out, ntg_parse_error* err) {
     ntg_ctx* ctx = s->ctx;
     if (s->finished) return ntg_set_error(ctx, NTG_EINVAL, "stream already finished");
@@ -220,7 +238,9 @@ static int stream_finish(ntg_stream* s, ntg_tallies* out, ntg_parse_error* err) 
     if (err) std::memset(err, 0, sizeof(*err));
     struct Done { ntg_stream* s; ~Done() { s->finished = true; } } done{s};
     NTG_TRY(gz_finish(s));
+    if (s->devgz) NTG_TRY(devgz_finish(s));
     if (!s->io_error.empty()) { if (err) err->kind = NTG_EIO; return ntg_set_error(ctx, NTG_OK, "%s", s->io_error.c_str()); }
+    if (!s->devgz) NTG_TRY(stream_need_staging(s));
     uint8_t* cur = s->pin[s->feed.L % NPIN];
     if (!s->opened && !s->unsupported) {
         // a stream shorter than one staging buffer: the sniff rules of parse_fastx_reader (mod.rs:85-93,37-46)
@@ -231,7 +251,9 @@ static int stream_finish(ntg_stream* s, ntg_tallies* out, ntg_parse_error* err) 
     if (s->unsupported && s->unsupported_flags == fused::FLAG_FORMAT && !s->opened) { if (err) err->kind = NTG_EUNKNOWN_FORMAT; return NTG_OK; }
     if (err) err->format = s->format;
     auto check = [&](uint64_t j, const LaunchCtl& c) { return stream_check(s, j, c); };
-    if (!s->failed && !s->unsupported) {
+    if (s->devgz) {
+        // (devgz_finish has launched the last batch)
+    } else if (!s->failed && !s->unsupported) {
         const uint64_t n_total = s->submitted_bytes + s->fill;
         s->in_submit = true;
         const int rc = s->feed.submit(cur, s->fill, true, n_total, check);
@@ -261,32 +283,13 @@ static int stream_finish(ntg_stream* s, ntg_tallies* out, ntg_parse_error* err) 
 }
 
 // ============================================================================================ gzip in front of a session
-// BGZF (SAM spec 4.1): every member is a gzip member whose extra field carries 'B','C',2,BSIZE-1; its last four bytes are ISIZE.
-// Header of the member at p: 0 = not BGZF, -1 = need more bytes, else the member's compressed size.
-static long bgzf_member_size(const uint8_t* p, size_t n) {
-    if (n < 12) return -1;
-    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
-    const size_t xlen = p[10] | (p[11] << 8);
-    if (12 + xlen > n) return -1;
-    for (size_t o = 12; o + 4 <= 12 + xlen;) {
-        const size_t slen = p[o + 2] | (p[o + 3] << 8);
-        if (p[o] == 'B' && p[o + 1] == 'C' && slen == 2 && o + 6 <= 12 + xlen) {
-            const size_t bs = (size_t)(p[o + 4] | (p[o + 5] << 8)) + 1;
-            return bs < 12 + xlen + 8 ? 0 : (long)bs;
-        }
-        o += 4 + slen;
-    }
-    return 0;
-}
-static uint32_t bgzf_isize(const uint8_t* p, size_t csize) {
-    return (uint32_t)p[csize - 4] | ((uint32_t)p[csize - 3] << 8) | ((uint32_t)p[csize - 2] << 16) | ((uint32_t)p[csize - 1] << 24);
-}
 // raw-deflate payload of one complete BGZF member -> dst (exactly isize bytes)
 static bool bgzf_inflate_member(const uint8_t* p, size_t csize, uint8_t* dst, uint32_t isize) {
-    const size_t xlen = p[10] | (p[11] << 8), hdr = 12 + xlen;
+    size_t hdr, plen;
+    if (!bgzf_payload(p, csize, &hdr, &plen)) return false;
     z_stream z; std::memset(&z, 0, sizeof(z));
     if (inflateInit2(&z, -15) != Z_OK) return false;
-    z.next_in = const_cast<Bytef*>(p + hdr); z.avail_in = (uInt)(csize - hdr - 8);
+    z.next_in = const_cast<Bytef*>(p + hdr); z.avail_in = (uInt)plen;
     z.next_out = dst; z.avail_out = isize;
     const int rc = isize ? inflate(&z, Z_FINISH) : Z_STREAM_END;
     const bool ok = rc == Z_STREAM_END && z.total_out == isize;
@@ -408,16 +411,182 @@ static int gz_feed_bgzf(ntg_stream* s, const uint8_t* in, size_t n, int threads)
     return NTG_OK;
 }
 
+
+// ============================================================================================ device-side inflate (BGZF)
+// The host walks the member headers and stages the raw DEFLATE payloads (pinned, double-buffered) with a member table; per
+// batch of ~DEVGZ_BATCH text bytes the payloads go to the device and gzdev::k_inflate writes the text into the next device
+// segment behind the bytes left over from the previous launch (a launch covers whole tiles); then the fused kernel runs.
+constexpr size_t DEVGZ_BATCH = size_t(512) << 20;               // text bytes per launch (8 192 members of 64 KiB)
+struct DevGz {
+    size_t comp_cap = 0; uint32_t mem_cap = 0;
+    uint8_t* h_comp[2] = {}; gzdev::Member* h_mem[2] = {};
+    uint8_t* d_comp[2] = {}; gzdev::Member* d_mem[2] = {};
+    uint32_t* d_err = nullptr;
+    cudaEvent_t ev_free[2] = {};
+    bool busy[2] = {false, false};
+    int cur = 0;
+    size_t comp_fill = 0; uint32_t n_mem = 0;
+    uint64_t text_fill = 0;                                      // text bytes the staged members will produce
+    size_t carry = 0;                                            // text bytes left over from the previous launch
+    std::vector<uint8_t> partial;                                // an incomplete member from the previous piece
+    std::vector<uint8_t> sample;                                 // the first text bytes (inflated on the host): format sniff + tile size
+    uint64_t text_total = 0;
+};
+static void devgz_free(DevGz* d) {
+    if (!d) return;
+    for (int i = 0; i < 2; i++) { cudaFreeHost(d->h_comp[i]); cudaFreeHost(d->h_mem[i]); cudaFree(d->d_comp[i]); cudaFree(d->d_mem[i]); if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]); }
+    cudaFree(d->d_err);
+    delete d;
+}
+static int devgz_init(ntg_stream* s) {
+    ntg_ctx* ctx = s->ctx;
+    auto* d = new DevGz();
+    s->devgz = d;
+    d->comp_cap = DEVGZ_BATCH + (size_t(1) << 20);               // (DEFLATE never expands a BGZF member beyond its 64 KiB limit)
+    d->mem_cap = (uint32_t)(DEVGZ_BATCH >> 10);                  // a batch also closes after this many members (tiny members)
+    for (int i = 0; i < 2; i++) {
+        if (cudaMallocHost((void**)&d->h_comp[i], d->comp_cap) != cudaSuccess || cudaMallocHost((void**)&d->h_mem[i], d->mem_cap * sizeof(gzdev::Member)) != cudaSuccess ||
+            cudaMalloc((void**)&d->d_comp[i], d->comp_cap) != cudaSuccess || cudaMalloc((void**)&d->d_mem[i], d->mem_cap * sizeof(gzdev::Member)) != cudaSuccess) {
+            cudaGetLastError();
+            return ntg_set_error(ctx, NTG_ENOMEM, "device-inflate staging allocation failed");
+        }
+        NTG_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming));
+    }
+    NTG_CUDA(ctx, cudaMalloc((void**)&d->d_err, sizeof(uint32_t)));
+    NTG_CUDA(ctx, cudaMemsetAsync(d->d_err, 0, sizeof(uint32_t), ctx->copy_stream));
+    return inflate_init(ctx);
+}
+// launch the staged members: H2D payloads + table, inflate into the next segment, fused kernel over its whole tiles
+static int devgz_flush(ntg_stream* s, bool final) {
+    ntg_ctx* ctx = s->ctx; DevGz* d = s->devgz;
+    if (s->failed || s->unsupported || !s->io_error.empty()) { d->comp_fill = 0; d->n_mem = 0; d->text_fill = 0; return NTG_OK; }
+    if (!s->opened) {
+        if (d->sample.empty()) {                                 // no text at all: the sniff rules see an empty stream
+            if (final) return NTG_OK;
+            return NTG_OK;
+        }
+        if (d->sample[0] != '>' && d->sample[0] != '@') { s->unsupported = true; s->unsupported_flags = fused::FLAG_FORMAT; return NTG_OK; }
+        s->format = d->sample[0] == '>' ? NTG_FMT_FASTA : NTG_FMT_FASTQ;
+        s->TB = pick_tile_bytes(d->sample.data(), d->sample.size() < 65536 ? d->sample.size() : 65536, s->format);
+        NTG_TRY(s->feed.open(ctx, s->format, &s->cfg, s->TB, true, DEVGZ_BATCH + (size_t(2) << 20)));
+        s->opened = true;
+    }
+    const uint64_t have = d->carry + d->text_fill;
+    if (have == 0 && !final) return NTG_OK;
+    const uint64_t ntiles = final ? (have + s->TB - 1) / s->TB : (have - 1) / s->TB;
+    const size_t len = final ? (size_t)have : (size_t)(ntiles * (uint64_t)s->TB);
+    if (!final && ntiles == 0) return NTG_OK;                    // (less than a tile so far: keep staging)
+    const int cur = d->cur;
+    const size_t comp_fill = d->comp_fill; const uint32_t n_mem = d->n_mem; const size_t carry = d->carry;
+    std::function<int(uint8_t*, const uint8_t*, size_t)> produce = [&](uint8_t* dst, const uint8_t* prev, size_t prev_len) -> int {
+        if (carry) NTG_CUDA(ctx, cudaMemcpyAsync(dst, prev + prev_len, carry, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        if (n_mem) {
+            NTG_CUDA(ctx, cudaMemcpyAsync(d->d_comp[cur], d->h_comp[cur], comp_fill, cudaMemcpyHostToDevice, ctx->copy_stream));
+            NTG_CUDA(ctx, cudaMemcpyAsync(d->d_mem[cur], d->h_mem[cur], n_mem * sizeof(gzdev::Member), cudaMemcpyHostToDevice, ctx->copy_stream));
+            NTG_TRY(inflate_enqueue(ctx, ctx->copy_stream, d->d_comp[cur], d->d_mem[cur], n_mem, dst, d->d_err));
+        }
+        NTG_CUDA(ctx, cudaEventRecord(d->ev_free[cur], ctx->copy_stream));
+        return NTG_OK;
+    };
+    auto check = [&](uint64_t j, const LaunchCtl& c) { return stream_check(s, j, c); };
+    const uint64_t n_total = s->submitted_bytes + have;
+    s->in_submit = true;
+    const int rc = s->feed.submit(nullptr, len, final, n_total, check, &produce);
+    s->in_submit = false;
+    NTG_TRY(rc);
+    d->busy[cur] = true;
+    s->submitted_bytes += len;
+    d->carry = (size_t)(have - len);
+    d->comp_fill = 0; d->n_mem = 0; d->text_fill = 0;
+    d->cur ^= 1;
+    if (d->busy[d->cur]) { NTG_CUDA(ctx, cudaEventSynchronize(d->ev_free[d->cur])); d->busy[d->cur] = false; }   // its staging is read no more
+    return NTG_OK;
+}
+// one complete member (csize bytes at p)
+static int devgz_member(ntg_stream* s, const uint8_t* p, size_t csize) {
+    DevGz* d = s->devgz;
+    size_t off, plen;
+    if (!bgzf_payload(p, csize, &off, &plen)) { s->io_error = "truncated BGZF member"; return NTG_OK; }
+    const uint32_t isize = bgzf_isize(p, csize);
+    if (isize > 65536) { s->io_error = "BGZF member larger than 64 KiB"; return NTG_OK; }
+    if (d->sample.size() < 65536 && isize) {                     // host inflate of the first members only: sniff + tile size
+        const size_t old = d->sample.size();
+        d->sample.resize(old + isize);
+        if (!bgzf_inflate_member(p, csize, d->sample.data() + old, isize)) { s->io_error = "inflate: corrupt BGZF member"; return NTG_OK; }
+    }
+    if (isize == 0) return NTG_OK;                               // (the BGZF end-of-file marker, empty members)
+    if (d->comp_fill + plen > d->comp_cap || d->n_mem == d->mem_cap || d->carry + d->text_fill + isize > DEVGZ_BATCH + (size_t(1) << 20))
+        NTG_TRY(devgz_flush(s, false));
+    std::memcpy(d->h_comp[d->cur] + d->comp_fill, p + off, plen);
+    d->h_mem[d->cur][d->n_mem++] = gzdev::Member{d->comp_fill, d->carry + d->text_fill, (uint32_t)plen, isize};
+    d->comp_fill += plen; d->text_fill += isize; d->text_total += isize; s->total_fed += isize;
+    if (d->carry + d->text_fill >= DEVGZ_BATCH) NTG_TRY(devgz_flush(s, false));
+    return NTG_OK;
+}
+static int devgz_feed(ntg_stream* s, const uint8_t* in, size_t n) {
+    DevGz* d = s->devgz;
+    size_t off = 0;
+    while (off < n && s->io_error.empty()) {
+        if (!d->partial.empty()) {
+            // complete the member that the previous piece left unfinished
+            const long ms = bgzf_member_size(d->partial.data(), d->partial.size());
+            if (ms == 0) { s->io_error = "not a BGZF member where one was expected"; break; }
+            const size_t need = ms < 0 ? d->partial.size() + 64 : (size_t)ms;
+            if (d->partial.size() < need) {
+                const size_t take = need - d->partial.size() < n - off ? need - d->partial.size() : n - off;
+                d->partial.insert(d->partial.end(), in + off, in + off + take);
+                off += take;
+                continue;
+            }
+            if (ms < 0) continue;
+            NTG_TRY(devgz_member(s, d->partial.data(), (size_t)ms));
+            d->partial.clear();
+            continue;
+        }
+        const long ms = bgzf_member_size(in + off, n - off);
+        if (ms == 0) {
+            if (in[off] == 0) { off = n; break; }                // zero padding behind the last member
+            s->io_error = "not a BGZF member where one was expected"; break;
+        }
+        if (ms < 0 || (size_t)ms > n - off) { d->partial.assign(in + off, in + n); off = n; break; }
+        NTG_TRY(devgz_member(s, in + off, (size_t)ms));
+        off += (size_t)ms;
+    }
+    return NTG_OK;
+}
+static int devgz_finish(ntg_stream* s) {
+    ntg_ctx* ctx = s->ctx; DevGz* d = s->devgz;
+    if (!d->partial.empty() && s->io_error.empty()) s->io_error = "gzip stream ends inside a member";
+    if (!s->io_error.empty()) return NTG_OK;
+    if (!s->opened && d->sample.size() < 2) {                    // the whole text is shorter than two bytes: host-side sniff rules below
+        NTG_TRY(stream_need_staging(s));
+        std::memcpy(s->pin[0], d->sample.data(), d->sample.size());
+        s->fill = d->sample.size();
+        devgz_free(d); s->devgz = nullptr;
+        return NTG_OK;
+    }
+    NTG_TRY(devgz_flush(s, true));
+    uint32_t e = 0;
+    NTG_CUDA(ctx, cudaMemcpyAsync(&e, d->d_err, sizeof(e), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (e) s->io_error = "inflate: corrupt BGZF member (device), code " + std::to_string(e & 31u);
+    return NTG_OK;
+}
+
 // One more piece of a gzip stream.  threads > 1 and a BGZF first member: block-parallel inflate; else sequential.
+// threads == 0 and BGZF: the members are inflated on the device (NTG_GZ_DEVICE).
 static int stream_feed_gz(ntg_stream* s, const uint8_t* in, size_t n, int threads) {
     if (!s->gz) s->gz = new GzState();
     GzState* g = s->gz;
     if (!n || !s->io_error.empty()) return NTG_OK;
     if (!g->decided) {
         // (a first piece too short to show the extra field is taken as plain gzip)
-        g->bgzf = threads > 1 && bgzf_member_size(in, n) > 0;
+        const bool is_bgzf = bgzf_member_size(in, n) > 0;
+        g->bgzf = threads > 1 && is_bgzf;
         g->decided = true;
+        if (threads == 0 && is_bgzf && s->total_fed == 0 && !s->opened) NTG_TRY(devgz_init(s));
     }
+    if (s->devgz) return devgz_feed(s, in, n);
     return g->bgzf ? gz_feed_bgzf(s, in, n, threads) : gz_feed_sequential(s, in, n);
 }
 static int gz_finish(ntg_stream* s) {

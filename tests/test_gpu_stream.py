@@ -220,3 +220,91 @@ def test_parse_chunks_equal_whole_parse(ctx, fixtures):
             assert np.array_equal(table, whole.table)
             if whole.err_kind:
                 assert (got.err_line, got.err_id) == (whole.err_line, whole.err_id)
+
+
+# ------------------------------------------------------------------ DEFLATE on the device (BGZF)
+def bgzf_with(data, level, strategy=0, block=0xFF00):
+    """BGZF members with a chosen zlib level / strategy (0 = stored blocks, Z_FIXED = fixed Huffman codes, ...)."""
+    import struct, zlib
+    out = []
+    for o in range(0, len(data), block):
+        chunk = bytes(data[o:o + block])
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+        payload = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(payload) + 8
+        assert bsize <= 0x10000
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + payload
+                   + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
+
+
+def test_device_inflate_matches_zlib(ctx):
+    import zlib
+    import needletail_b200 as nt
+    from needletail_b200 import bgzf
+    rng = random.Random(23)
+    texts = [fastq(rng, 3000, 150), bytes(rng.randrange(256) for _ in range(200_000)), b"A" * 300_000, b"", b"x",
+             bytes(rng.choice(b"ACGT") for _ in range(150_000)), (b"ACGTTGCA" * 40 + b"\n") * 800]
+    for ti, text in enumerate(texts):
+        for level, strategy, block in ((1, 0, 0xFF00), (6, 0, 0xFF00), (9, 0, 0x8000), (0, 0, 0xFF00 - 64), (6, zlib.Z_FIXED, 0xFF00),
+                                       (6, zlib.Z_HUFFMAN_ONLY, 0x4000), (6, zlib.Z_RLE, 0xFF00), (1, 0, 100)):
+            blob = bgzf_with(text, level, strategy, block) + bgzf.EOF_MARKER
+            assert ctx.inflate_bgzf(blob) == text, (ti, level, strategy, block)
+    # corrupt payloads are I/O errors, never out-of-bounds writes
+    blob = bytearray(bgzf_with(texts[0], 6))
+    for pos in (30, 200, 5000, len(blob) // 2):
+        bad = bytearray(blob); bad[pos] ^= 0x5A
+        try:
+            got = ctx.inflate_bgzf(bytes(bad))
+        except nt.NtgError:
+            continue
+        assert len(got) == len(texts[0])                          # (a flipped bit may still decode to the right length)
+
+
+def test_device_inflate_in_the_tally_session(ctx):
+    from needletail_b200 import bgzf
+    rng = random.Random(29)
+    data = fastq(rng, 9000, 150)
+    exp = O.tally_fastx(data, k=31, m=21)
+    bg = bgzf.compress(data)
+    for cut in (None, 1 << 16, 4093):
+        s = ctx.stream(k=31, m=21)
+        if cut is None:
+            s.feed_gz(bg, 0)
+        else:
+            for o in range(0, len(bg), cut):
+                s.feed_gz(bg[o:o + cut], 0)
+        got = s.finish()
+        same(got, exp, f"device inflate cut={cut}")
+    # errors inside the text keep their iterator semantics
+    pos = data.index(b"@r4500 ")
+    bad = data[:pos] + data[pos:].replace(b"\n+\n", b"\n-\n", 1)
+    s = ctx.stream(k=31, m=21); s.feed_gz(bgzf.compress(bad), 0); got = s.finish()
+    same(got, O.tally_fastx(bad, k=31, m=21), "device inflate + parse error")
+    assert got["err_line"] == O.parse_fastx(bad).err_line
+    # tiny and empty texts, FASTA, unknown format, truncated file
+    for text in (b"", b">", b">a\nACGT\n", b"hello\n"):
+        s = ctx.stream(k=3); s.feed_gz(bgzf.compress(text), 0)
+        same(s.finish(), O.tally_fastx(text, k=3), repr(text))
+    s = ctx.stream(k=31); s.feed_gz(bg[:len(bg) // 2], 0)
+    assert s.finish()["err_kind"] == "Io"
+    # a few hundred MB: several 512 MiB-text batches are not needed to cross launches — force it with many members
+    L, nrec = 150, 2_000_000
+    d = ctx.device_alloc(nrec * (2 * L + 16))
+    ctx.synth_fastq_device(d, 0x5EED0002, 0, nrec, L, 0)
+    exp = ctx.tally_device(d, nrec * (2 * L + 16), k=31, m=21)
+    host = ctx.d2h(d, nrec * (2 * L + 16)); ctx.device_free(d)
+    blob = bgzf.compress(host[: 64 << 20].tobytes())                # 64 MiB of text compressed once ...
+    reps = (nrec * (2 * L + 16)) // (64 << 20)
+    s = ctx.stream(k=31, m=21)
+    for _ in range(reps * 9):                                        # ... fed often enough for two 512 MiB batches
+        s.feed_gz(blob[:-28], 0)                                     # (without the EOF marker)
+    got = s.finish()
+    one = ctx.tally(host[: 64 << 20], k=31, m=21)
+    # the 64 MiB block ends inside a record, so the concatenation is not 9*reps copies of valid text: compare with the host inflate
+    s = ctx.stream(k=31, m=21)
+    for _ in range(reps * 9):
+        s.feed_gz(blob[:-28], 4)
+    ref = s.finish()
+    same(got, ref, "device vs host inflate, multi-batch")
+    assert one["n_records"] > 0
