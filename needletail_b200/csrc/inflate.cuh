@@ -28,8 +28,11 @@ struct Member {
 struct Bits {
     const uint8_t* p; const uint8_t* end;
     uint64_t buf; uint32_t cnt; uint32_t err;
+    // bytes up to the next 4-byte boundary, then one aligned 32-bit load per refill (the tail of the payload by bytes again)
     __device__ __forceinline__ void refill() {
-        while (cnt <= 56 && p < end) { buf |= (uint64_t)(*p++) << cnt; cnt += 8; }
+        while (cnt <= 56 && p < end && ((uintptr_t)p & 3u)) { buf |= (uint64_t)(*p++) << cnt; cnt += 8; }
+        if (cnt <= 32 && p + 4 <= end) { buf |= (uint64_t)(*reinterpret_cast<const uint32_t*>(p)) << cnt; p += 4; cnt += 32; }
+        else if (p + 4 > end) while (cnt <= 56 && p < end) { buf |= (uint64_t)(*p++) << cnt; cnt += 8; }
     }
     __device__ __forceinline__ uint32_t take(uint32_t n) {          // n <= 16
         if (cnt < n) { refill(); if (cnt < n) { err = 1; cnt = 0; buf = 0; return 0; } }
@@ -97,28 +100,31 @@ __global__ void __launch_bounds__(THREADS) k_inflate(const uint8_t* __restrict__
     uint32_t bad = 0;
     uint8_t lengths[MAXL + MAXD + 2];
     Counts lc, dc;
-    for (;;) {
+    // Control flow note: no `break` out of a divergent branch.  A branch that can leave the loop has its reconvergence point
+    // behind the loop, so lanes that once took different sides (literal / match) would never rejoin and the warp would run
+    // its 32 members one after the other (measured: 73 MB/s).  Every exit goes through a flag tested at the loop head.
+    bool more = true;
+    while (more && !bad) {
         const uint32_t last = b.take(1), type = b.take(2);
-        if (b.err) { bad = 1; break; }
-        if (type == 0) {
+        if (b.err) bad = 1;
+        else if (type == 0) {
             // stored block: to the byte boundary, LEN, ~LEN, LEN raw bytes
             const uint32_t drop = b.cnt & 7u;
             b.buf >>= drop; b.cnt -= drop;
             const uint32_t len = b.take(16), nlen = b.take(16);
-            if (b.err || (len ^ 0xFFFFu) != nlen || pos + len > m.out_len) { bad = 2; break; }
-            for (uint32_t i = 0; i < len; i++) {
-                uint32_t v;
+            if (b.err || (len ^ 0xFFFFu) != nlen || pos + len > m.out_len) bad = 2;
+            for (uint32_t i = 0; i < len && !bad; i++) {
+                uint32_t v = 0;
                 if (b.cnt >= 8) { v = (uint32_t)b.buf & 0xFFu; b.buf >>= 8; b.cnt -= 8; }
                 else if (b.p < b.end) v = *b.p++;
-                else { bad = 3; break; }
-                o[pos++] = (uint8_t)v;
+                else bad = 3;
+                if (!bad) o[pos++] = (uint8_t)v;
             }
-            if (bad) break;
-        } else if (type == 1 || type == 2) {
-            int nlen, ndist;
+        } else if (type == 3) bad = 17;
+        else {
+            int nlen = 288, ndist = 30;
             if (type == 1) {
                 // fixed code (RFC 1951 3.2.6)
-                nlen = 288; ndist = 30;
                 for (int s = 0; s < 144; s++) lengths[s] = 8;
                 for (int s = 144; s < 256; s++) lengths[s] = 9;
                 for (int s = 256; s < 280; s++) lengths[s] = 7;
@@ -127,65 +133,84 @@ __global__ void __launch_bounds__(THREADS) k_inflate(const uint8_t* __restrict__
             } else {
                 nlen = (int)b.take(5) + 257; ndist = (int)b.take(5) + 1;
                 const int ncode = (int)b.take(4) + 4;
-                if (b.err || nlen > 286 || ndist > 30) { bad = 4; break; }
+                if (b.err || nlen > 286 || ndist > 30) { bad = 4; nlen = 257; ndist = 1; }
                 // code-length code: 19 symbols in the order of 3.2.7; its table uses the distance slot until the real one is built
                 for (int i = 0; i < 19; i++) lengths[i] = 0;
-                for (int i = 0; i < ncode; i++) {
+                for (int i = 0; i < ncode && !bad; i++) {
                     // 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
                     const int sym_i = i < 3 ? 16 + i : (i == 3 ? 0 : ((i & 1) ? 7 - ((i - 5) >> 1) : 8 + ((i - 4) >> 1)));
                     lengths[sym_i] = (uint8_t)b.take(3);
                 }
                 Counts cc;
-                if (b.err || !build(lengths, 19, cc, dsym, THREADS)) { bad = 5; break; }
+                if (!bad && (b.err || !build(lengths, 19, cc, dsym, THREADS))) bad = 5;
                 int idx = 0;
-                while (idx < nlen + ndist) {
-                    int s = decode(b, cc, dsym, THREADS);
-                    if (s < 0) { bad = 6; break; }
-                    if (s < 16) lengths[idx++] = (uint8_t)s;
+                while (idx < nlen + ndist && !bad) {
+                    const int s = decode(b, cc, dsym, THREADS);
+                    if (s < 0) bad = 6;
+                    else if (s < 16) lengths[idx++] = (uint8_t)s;
                     else {
                         int rep, val = 0;
-                        if (s == 16) { if (idx == 0) { bad = 7; break; } val = lengths[idx - 1]; rep = 3 + (int)b.take(2); }
+                        if (s == 16) { if (idx == 0) bad = 7; else val = lengths[idx - 1]; rep = 3 + (int)b.take(2); }
                         else if (s == 17) rep = 3 + (int)b.take(3);
                         else rep = 11 + (int)b.take(7);
-                        if (idx + rep > nlen + ndist) { bad = 8; break; }
-                        while (rep--) lengths[idx++] = (uint8_t)val;
+                        if (idx + rep > nlen + ndist) bad = 8;
+                        for (; rep > 0 && !bad; rep--) lengths[idx++] = (uint8_t)val;
                     }
                 }
-                if (bad || b.err) { bad = bad ? bad : 9; break; }
-                if (lengths[256] == 0) { bad = 10; break; }                // no end-of-block code
+                if (!bad && b.err) bad = 9;
+                if (!bad && lengths[256] == 0) bad = 10;                   // no end-of-block code
             }
-            // move the distance lengths out of the way of build() (it reads lengths[0..n))
-            uint8_t dl[MAXD];
-            for (int s = 0; s < ndist; s++) dl[s] = lengths[nlen + s];
-            if (!build(lengths, nlen, lc, lsym, THREADS) || !build(dl, ndist, dc, dsym, THREADS)) { bad = 11; break; }
-            for (;;) {
+            if (!bad) {
+                // move the distance lengths out of the way of build() (it reads lengths[0..n))
+                uint8_t dl[MAXD];
+                for (int s = 0; s < ndist; s++) dl[s] = lengths[nlen + s];
+                if (!build(lengths, nlen, lc, lsym, THREADS) || !build(dl, ndist, dc, dsym, THREADS)) bad = 11;
+            }
+            bool in_block = !bad;
+            while (in_block) {
                 int s = decode(b, lc, lsym, THREADS);
-                if (s < 0) { bad = 12; break; }
-                if (s < 256) {
-                    if (pos >= m.out_len) { bad = 13; break; }
-                    o[pos++] = (uint8_t)s;
-                } else if (s == 256) break;
+                if (s < 0) { bad = 12; in_block = false; }
+                else if (s < 256) {
+                    if (pos >= m.out_len) { bad = 13; in_block = false; }
+                    else o[pos++] = (uint8_t)s;
+                } else if (s == 256) in_block = false;
                 else {
                     s -= 257;
-                    if (s >= 29) { bad = 14; break; }
-                    uint32_t len;
-                    if (s < 8) len = 3 + s;
-                    else if (s == 28) len = 258;
-                    else { const int e = (s - 4) >> 2; len = 3 + ((4 + (s & 3)) << e) + b.take(e); }
-                    const int ds = decode(b, dc, dsym, THREADS);
-                    if (ds < 0 || ds >= 30) { bad = 15; break; }
-                    uint32_t dist;
-                    if (ds < 4) dist = 1 + ds;
-                    else { const int e = (ds - 2) >> 1; dist = 1 + ((2 + (ds & 1)) << e) + b.take(e); }
-                    if (b.err || dist > pos || pos + len > m.out_len) { bad = 16; break; }
-                    const uint8_t* src = o + pos - dist;
-                    for (uint32_t i = 0; i < len; i++) o[pos + i] = src[i];      // forward byte copy: overlapping runs repeat
-                    pos += len;
+                    uint32_t len = 0, dist = 0;
+                    if (s >= 29) bad = 14;
+                    else {
+                        if (s < 8) len = 3 + s;
+                        else if (s == 28) len = 258;
+                        else { const int e = (s - 4) >> 2; len = 3 + ((4 + (s & 3)) << e) + b.take(e); }
+                        const int ds = decode(b, dc, dsym, THREADS);
+                        if (ds < 0 || ds >= 30) bad = 15;
+                        else {
+                            if (ds < 4) dist = 1 + ds;
+                            else { const int e = (ds - 2) >> 1; dist = 1 + ((2 + (ds & 1)) << e) + b.take(e); }
+                            if (b.err || dist > pos || pos + len > m.out_len) bad = 16;
+                        }
+                    }
+                    if (bad) in_block = false;
+                    else {
+                        // The source bytes were written by this thread a moment ago and live in L2 (stores do not allocate in
+                        // L1): a byte-by-byte copy pays one L2 round trip per byte.  Chunks of up to 8 bytes, never longer than
+                        // `dist` (so a chunk's sources are older than its destinations): all loads of a chunk are in flight together.
+                        const uint8_t* src = o + pos - dist;
+                        for (uint32_t i = 0; i < len;) {
+                            uint32_t c = len - i; c = c < 8u ? c : 8u; c = c < dist ? c : dist;
+                            uint8_t t[8];
+#pragma unroll
+                            for (uint32_t j = 0; j < 8; j++) if (j < c) t[j] = src[i + j];
+#pragma unroll
+                            for (uint32_t j = 0; j < 8; j++) if (j < c) o[pos + i + j] = t[j];
+                            i += c;
+                        }
+                        pos += len;
+                    }
                 }
             }
-            if (bad) break;
-        } else { bad = 17; break; }
-        if (last) break;
+        }
+        if (last) more = false;
     }
     if (!bad && pos != m.out_len) bad = 18;
     if (bad) atomicMax(errors, (g << 5) | bad | 0x80000000u);

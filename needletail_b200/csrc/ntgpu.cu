@@ -487,6 +487,7 @@ int ntg_inflate_bgzf(ntg_ctx* ctx, const uint8_t* gz, size_t n, uint8_t* out, si
         if (!bgzf_payload(gz + off, (size_t)ms, &po, &pl)) return ntg_set_error(ctx, NTG_EIO, "truncated BGZF member at offset %zu", off);
         const uint32_t isize = bgzf_isize(gz + off, (size_t)ms);
         if (isize) {
+            payload.resize((payload.size() + 3) & ~size_t(3));          // (aligned 32-bit refills)
             members.push_back(gzdev::Member{payload.size(), text, (uint32_t)pl, isize});
             payload.insert(payload.end(), gz + off + po, gz + off + po + pl);
             text += isize;
@@ -499,7 +500,7 @@ int ntg_inflate_bgzf(ntg_ctx* ctx, const uint8_t* gz, size_t n, uint8_t* out, si
     if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output");
     NTG_TRY(inflate_init(ctx));
     DevBuf<uint8_t> d_comp, d_out; DevBuf<gzdev::Member> d_mem; DevBuf<uint32_t> d_err;
-    if (d_comp.alloc(payload.size()) || d_out.alloc(text) || d_mem.alloc(members.size()) || d_err.alloc(1)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    if (d_comp.alloc(payload.size() + 8) || d_out.alloc(text) || d_mem.alloc(members.size()) || d_err.alloc(1)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     NTG_CUDA(ctx, cudaMemcpyAsync(d_comp.p, payload.data(), payload.size(), cudaMemcpyHostToDevice, ctx->stream));
     NTG_CUDA(ctx, cudaMemcpyAsync(d_mem.p, members.data(), members.size() * sizeof(gzdev::Member), cudaMemcpyHostToDevice, ctx->stream));
     NTG_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), ctx->stream));

@@ -413,16 +413,18 @@ static int gz_feed_bgzf(ntg_stream* s, const uint8_t* in, size_t n, int threads)
 
 
 // ============================================================================================ device-side inflate (BGZF)
-// The host walks the member headers and stages the raw DEFLATE payloads (pinned, double-buffered) with a member table; per
-// batch of ~DEVGZ_BATCH text bytes the payloads go to the device and gzdev::k_inflate writes the text into the next device
-// segment behind the bytes left over from the previous launch (a launch covers whole tiles); then the fused kernel runs.
-constexpr size_t DEVGZ_BATCH = size_t(512) << 20;               // text bytes per launch (8 192 members of 64 KiB)
+// The host only walks the member headers.  The compressed bytes of every piece go to the device as they are fed (one H2D per
+// run of members, straight from the caller's buffer: pin it for full PCIe speed), the member table follows per batch of
+// ~DEVGZ_BATCH text bytes, and gzdev::k_inflate writes the text into the next device segment behind the bytes left over from
+// the previous launch (a launch covers whole tiles); then the fused kernel runs.  A batch is large because one THREAD inflates
+// one member: 2 GiB of text are 32 768 members, about the number of threads the decoder keeps resident.
+constexpr size_t DEVGZ_BATCH = size_t(2) << 30;
 struct DevGz {
     size_t comp_cap = 0; uint32_t mem_cap = 0;
-    uint8_t* h_comp[2] = {}; gzdev::Member* h_mem[2] = {};
-    uint8_t* d_comp[2] = {}; gzdev::Member* d_mem[2] = {};
+    uint8_t* d_comp[2] = {}; gzdev::Member* d_mem[2] = {}; gzdev::Member* h_mem[2] = {};     // h_mem pinned
     uint32_t* d_err = nullptr;
-    cudaEvent_t ev_free[2] = {};
+    cudaStream_t gz_stream = nullptr;                            // H2D of compressed bytes (the caller's buffer is free again when a feed returns)
+    cudaEvent_t ev_free[2] = {}, ev_h2d = nullptr;
     bool busy[2] = {false, false};
     int cur = 0;
     size_t comp_fill = 0; uint32_t n_mem = 0;
@@ -430,11 +432,12 @@ struct DevGz {
     size_t carry = 0;                                            // text bytes left over from the previous launch
     std::vector<uint8_t> partial;                                // an incomplete member from the previous piece
     std::vector<uint8_t> sample;                                 // the first text bytes (inflated on the host): format sniff + tile size
-    uint64_t text_total = 0;
 };
 static void devgz_free(DevGz* d) {
     if (!d) return;
-    for (int i = 0; i < 2; i++) { cudaFreeHost(d->h_comp[i]); cudaFreeHost(d->h_mem[i]); cudaFree(d->d_comp[i]); cudaFree(d->d_mem[i]); if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]); }
+    if (d->gz_stream) { cudaStreamSynchronize(d->gz_stream); cudaStreamDestroy(d->gz_stream); }
+    for (int i = 0; i < 2; i++) { cudaFreeHost(d->h_mem[i]); cudaFree(d->d_comp[i]); cudaFree(d->d_mem[i]); if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]); }
+    if (d->ev_h2d) cudaEventDestroy(d->ev_h2d);
     cudaFree(d->d_err);
     delete d;
 }
@@ -442,29 +445,28 @@ static int devgz_init(ntg_stream* s) {
     ntg_ctx* ctx = s->ctx;
     auto* d = new DevGz();
     s->devgz = d;
-    d->comp_cap = DEVGZ_BATCH + (size_t(1) << 20);               // (DEFLATE never expands a BGZF member beyond its 64 KiB limit)
-    d->mem_cap = (uint32_t)(DEVGZ_BATCH >> 10);                  // a batch also closes after this many members (tiny members)
+    d->comp_cap = DEVGZ_BATCH + (size_t(16) << 20);              // (a member is at most 64 KiB compressed, like its text; headers travel too)
+    d->mem_cap = (uint32_t)(DEVGZ_BATCH >> 12);                  // a batch also closes after this many members (small members)
     for (int i = 0; i < 2; i++) {
-        if (cudaMallocHost((void**)&d->h_comp[i], d->comp_cap) != cudaSuccess || cudaMallocHost((void**)&d->h_mem[i], d->mem_cap * sizeof(gzdev::Member)) != cudaSuccess ||
+        if (cudaMallocHost((void**)&d->h_mem[i], d->mem_cap * sizeof(gzdev::Member)) != cudaSuccess ||
             cudaMalloc((void**)&d->d_comp[i], d->comp_cap) != cudaSuccess || cudaMalloc((void**)&d->d_mem[i], d->mem_cap * sizeof(gzdev::Member)) != cudaSuccess) {
             cudaGetLastError();
             return ntg_set_error(ctx, NTG_ENOMEM, "device-inflate staging allocation failed");
         }
         NTG_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming));
     }
+    NTG_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_h2d, cudaEventDisableTiming));
+    NTG_CUDA(ctx, cudaStreamCreateWithFlags(&d->gz_stream, cudaStreamNonBlocking));
     NTG_CUDA(ctx, cudaMalloc((void**)&d->d_err, sizeof(uint32_t)));
     NTG_CUDA(ctx, cudaMemsetAsync(d->d_err, 0, sizeof(uint32_t), ctx->copy_stream));
     return inflate_init(ctx);
 }
-// launch the staged members: H2D payloads + table, inflate into the next segment, fused kernel over its whole tiles
+// launch the staged members: member table to the device, inflate into the next segment, fused kernel over its whole tiles
 static int devgz_flush(ntg_stream* s, bool final) {
     ntg_ctx* ctx = s->ctx; DevGz* d = s->devgz;
     if (s->failed || s->unsupported || !s->io_error.empty()) { d->comp_fill = 0; d->n_mem = 0; d->text_fill = 0; return NTG_OK; }
     if (!s->opened) {
-        if (d->sample.empty()) {                                 // no text at all: the sniff rules see an empty stream
-            if (final) return NTG_OK;
-            return NTG_OK;
-        }
+        if (d->sample.empty()) return NTG_OK;                    // no text yet
         if (d->sample[0] != '>' && d->sample[0] != '@') { s->unsupported = true; s->unsupported_flags = fused::FLAG_FORMAT; return NTG_OK; }
         s->format = d->sample[0] == '>' ? NTG_FMT_FASTA : NTG_FMT_FASTQ;
         s->TB = pick_tile_bytes(d->sample.data(), d->sample.size() < 65536 ? d->sample.size() : 65536, s->format);
@@ -477,11 +479,12 @@ static int devgz_flush(ntg_stream* s, bool final) {
     const size_t len = final ? (size_t)have : (size_t)(ntiles * (uint64_t)s->TB);
     if (!final && ntiles == 0) return NTG_OK;                    // (less than a tile so far: keep staging)
     const int cur = d->cur;
-    const size_t comp_fill = d->comp_fill; const uint32_t n_mem = d->n_mem; const size_t carry = d->carry;
+    const uint32_t n_mem = d->n_mem; const size_t carry = d->carry;
+    NTG_CUDA(ctx, cudaEventRecord(d->ev_h2d, d->gz_stream));    // every compressed byte of this batch has been enqueued
     std::function<int(uint8_t*, const uint8_t*, size_t)> produce = [&](uint8_t* dst, const uint8_t* prev, size_t prev_len) -> int {
         if (carry) NTG_CUDA(ctx, cudaMemcpyAsync(dst, prev + prev_len, carry, cudaMemcpyDeviceToDevice, ctx->copy_stream));
         if (n_mem) {
-            NTG_CUDA(ctx, cudaMemcpyAsync(d->d_comp[cur], d->h_comp[cur], comp_fill, cudaMemcpyHostToDevice, ctx->copy_stream));
+            NTG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, d->ev_h2d, 0));
             NTG_CUDA(ctx, cudaMemcpyAsync(d->d_mem[cur], d->h_mem[cur], n_mem * sizeof(gzdev::Member), cudaMemcpyHostToDevice, ctx->copy_stream));
             NTG_TRY(inflate_enqueue(ctx, ctx->copy_stream, d->d_comp[cur], d->d_mem[cur], n_mem, dst, d->d_err));
         }
@@ -499,11 +502,22 @@ static int devgz_flush(ntg_stream* s, bool final) {
     d->carry = (size_t)(have - len);
     d->comp_fill = 0; d->n_mem = 0; d->text_fill = 0;
     d->cur ^= 1;
-    if (d->busy[d->cur]) { NTG_CUDA(ctx, cudaEventSynchronize(d->ev_free[d->cur])); d->busy[d->cur] = false; }   // its staging is read no more
+    // the other staging pair: its compressed bytes and table may be overwritten once the inflate that read them is done
+    if (d->busy[d->cur]) { NTG_CUDA(ctx, cudaStreamWaitEvent(d->gz_stream, d->ev_free[d->cur], 0)); NTG_CUDA(ctx, cudaEventSynchronize(d->ev_free[d->cur])); d->busy[d->cur] = false; }
     return NTG_OK;
 }
-// one complete member (csize bytes at p)
-static int devgz_member(ntg_stream* s, const uint8_t* p, size_t csize) {
+// a run of complete members [p, p + bytes) of the caller's buffer: table entries + one H2D copy
+struct DevGzRun { const uint8_t* p = nullptr; size_t bytes = 0; };
+static int devgz_send_run(ntg_stream* s, DevGzRun& run) {
+    DevGz* d = s->devgz;
+    if (!run.bytes) return NTG_OK;
+    NTG_CUDA(s->ctx, cudaMemcpyAsync(d->d_comp[d->cur] + d->comp_fill, run.p, run.bytes, cudaMemcpyHostToDevice, d->gz_stream));
+    d->comp_fill += run.bytes;
+    run = DevGzRun{};
+    return NTG_OK;
+}
+// one complete member (csize bytes at p): joins the current run (or starts one)
+static int devgz_member(ntg_stream* s, const uint8_t* p, size_t csize, DevGzRun& run) {
     DevGz* d = s->devgz;
     size_t off, plen;
     if (!bgzf_payload(p, csize, &off, &plen)) { s->io_error = "truncated BGZF member"; return NTG_OK; }
@@ -514,18 +528,24 @@ static int devgz_member(ntg_stream* s, const uint8_t* p, size_t csize) {
         d->sample.resize(old + isize);
         if (!bgzf_inflate_member(p, csize, d->sample.data() + old, isize)) { s->io_error = "inflate: corrupt BGZF member"; return NTG_OK; }
     }
-    if (isize == 0) return NTG_OK;                               // (the BGZF end-of-file marker, empty members)
-    if (d->comp_fill + plen > d->comp_cap || d->n_mem == d->mem_cap || d->carry + d->text_fill + isize > DEVGZ_BATCH + (size_t(1) << 20))
+    if (d->comp_fill + run.bytes + csize + 8 > d->comp_cap || d->n_mem == d->mem_cap || d->carry + d->text_fill + isize > DEVGZ_BATCH + (size_t(1) << 20)) {
+        NTG_TRY(devgz_send_run(s, run));
         NTG_TRY(devgz_flush(s, false));
-    std::memcpy(d->h_comp[d->cur] + d->comp_fill, p + off, plen);
-    d->h_mem[d->cur][d->n_mem++] = gzdev::Member{d->comp_fill, d->carry + d->text_fill, (uint32_t)plen, isize};
-    d->comp_fill += plen; d->text_fill += isize; d->text_total += isize; s->total_fed += isize;
-    if (d->carry + d->text_fill >= DEVGZ_BATCH) NTG_TRY(devgz_flush(s, false));
+    }
+    if (run.bytes && run.p + run.bytes != p) NTG_TRY(devgz_send_run(s, run));
+    if (!run.bytes) run.p = p;
+    if (isize) {
+        d->h_mem[d->cur][d->n_mem++] = gzdev::Member{d->comp_fill + run.bytes + off, d->carry + d->text_fill, (uint32_t)plen, isize};
+        d->text_fill += isize; s->total_fed += isize;
+    }
+    run.bytes += csize;
+    if (d->carry + d->text_fill >= DEVGZ_BATCH) { NTG_TRY(devgz_send_run(s, run)); NTG_TRY(devgz_flush(s, false)); }
     return NTG_OK;
 }
 static int devgz_feed(ntg_stream* s, const uint8_t* in, size_t n) {
     DevGz* d = s->devgz;
     size_t off = 0;
+    DevGzRun run;
     while (off < n && s->io_error.empty()) {
         if (!d->partial.empty()) {
             // complete the member that the previous piece left unfinished
@@ -539,7 +559,10 @@ static int devgz_feed(ntg_stream* s, const uint8_t* in, size_t n) {
                 continue;
             }
             if (ms < 0) continue;
-            NTG_TRY(devgz_member(s, d->partial.data(), (size_t)ms));
+            DevGzRun one;
+            NTG_TRY(devgz_member(s, d->partial.data(), (size_t)ms, one));
+            NTG_TRY(devgz_send_run(s, one));
+            NTG_CUDA(s->ctx, cudaStreamSynchronize(d->gz_stream));      // (the copy reads `partial`)
             d->partial.clear();
             continue;
         }
@@ -549,9 +572,11 @@ static int devgz_feed(ntg_stream* s, const uint8_t* in, size_t n) {
             s->io_error = "not a BGZF member where one was expected"; break;
         }
         if (ms < 0 || (size_t)ms > n - off) { d->partial.assign(in + off, in + n); off = n; break; }
-        NTG_TRY(devgz_member(s, in + off, (size_t)ms));
+        NTG_TRY(devgz_member(s, in + off, (size_t)ms, run));
         off += (size_t)ms;
     }
+    NTG_TRY(devgz_send_run(s, run));
+    NTG_CUDA(s->ctx, cudaStreamSynchronize(d->gz_stream));             // the caller's buffer is free again
     return NTG_OK;
 }
 static int devgz_finish(ntg_stream* s) {
