@@ -129,6 +129,14 @@ void ntg_records_free(ntg_records* r);
  * `consumed`, so the caller carries  line_base += final_line - 1,  record_base += n_records,  byte_base += consumed. */
 int ntg_parse_fastx_chunk(ntg_ctx* ctx, const uint8_t* bytes, size_t n, int format, int at_eof, ntg_records** out, uint64_t* consumed);
 
+/* Record writers for filtered output: SequenceRecord::write / write_fasta / write_fastq (src/parser/record.rs:158-247) over a
+ * record table.  The text of every record i with keep[i] != 0 (keep == NULL: all), in table order, with the given line ending
+ * (NTG_LE_UNIX / NTG_LE_WINDOWS: the `forced_line_ending` of the reference): '>' id EOL raw_seq EOL, or '@' id EOL raw_seq EOL
+ * '+' EOL qual EOL.  `bytes` is the buffer the table indexes.  *out_len = bytes needed (also when out_cap is too small:
+ * NTG_EINVAL then, nothing written). */
+int ntg_write_records(ntg_ctx* ctx, const uint8_t* bytes, size_t n, int format, const ntg_record* records, size_t n_records,
+                      const uint8_t* keep, int line_ending, uint8_t* out, size_t out_cap, size_t* out_len);
+
 /* ---- (2) Sequence trait, batch form -----------------------------------------------------
  * Every call works on a batch of sequences so that one FFI crossing amortises over many
  * records (a per-k-mer FFI call would dominate).  */
@@ -270,6 +278,33 @@ void ntg_stream_close(ntg_stream* s);
  * inflating gzip on the way (`threads` workers for BGZF).  bzip2 / xz / zstd files: NTG_EUNSUPPORTED (zlib only). */
 int ntg_tally_fastx_file(ntg_ctx* ctx, const char* path, const ntg_tally_config* cfg, int threads,
                          ntg_tallies* out, ntg_parse_error* err);
+
+/* ---- (3c) k-mer spectrum: count per distinct canonical k-mer -------------------------------------
+ * The consumer of `canonical_kmers` (the README loop counts ONE k-mer: src/lib.rs:31-35).  Definition: the multiset
+ * of items of `rec.normalize(false).canonical_kmers(k, &rc)` over every record delivered before the first parse error, keyed by
+ * the 2-bit pack of the canonical k-mer (== bit_kmers(k, true)).  k <= 14: dense histogram of 4^k u32 counters (`capacity`
+ * ignored); 15 <= k <= 32: open-addressing hash table of `capacity` slots (rounded up to a power of two; NTG_ENOMEM when full).
+ * Counts saturate nowhere: they wrap at 2^32. */
+typedef struct ntg_spectrum ntg_spectrum;
+int ntg_spectrum_create(ntg_ctx* ctx, uint32_t k, uint64_t capacity, ntg_spectrum** out);
+void ntg_spectrum_destroy(ntg_spectrum* sp);
+int ntg_spectrum_clear(ntg_spectrum* sp);
+/* add every canonical k-mer of a FASTX input (host bytes of any size / bytes resident in HBM, 16-byte aligned).  tallies (may be
+ * NULL) receives the counting pass's tallies (n_kmers == k-mers added).  A parse error ends the input in front of the failing
+ * record (err->kind != 0; use ntg_tally_fastx for its exact kind / line). */
+int ntg_spectrum_add_fastx(ntg_spectrum* sp, const uint8_t* bytes, size_t n, ntg_tallies* tallies, ntg_parse_error* err);
+int ntg_spectrum_add_fastx_device(ntg_spectrum* sp, uint64_t dptr, size_t n, ntg_tallies* tallies, ntg_parse_error* err);
+/* count of one k-mer given as k ASCII bases ACGT (its canonical form is looked up) — the README example */
+int ntg_spectrum_count(ntg_spectrum* sp, const uint8_t* kmer, uint64_t* count);
+/* the distinct k-mers and their counts, in arbitrary order; *n_distinct is the full number also when cap is smaller */
+int ntg_spectrum_export(ntg_spectrum* sp, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_distinct);
+/* count-of-counts: hist[c] = number of distinct k-mers seen c times (c >= n_bins - 1 collected in the last bin) */
+int ntg_spectrum_histogram(ntg_spectrum* sp, uint64_t* hist, uint32_t n_bins);
+/* multi-GPU (after ntg_comm_init, same k / capacity on every rank).  Dense: ONE ncclAllReduce over the whole histogram, every rank
+ * ends with the job-wide counts.  Hash: entries travel to their owner rank (hash of the key) with grouped ncclSend / ncclRecv:
+ * every rank ends with the job-wide counts of the keys it owns (reduce-scatter by k-mer hash). */
+int ntg_spectrum_reduce(ntg_spectrum* sp);
+uint64_t ntg_spectrum_kmers(const ntg_spectrum* sp);             /* k-mers added on this rank so far */
 
 /* ---- (4) synthetic inputs (DESIGN.md "Synthetic inputs"; same bytes as oracle/synth.hpp) ---- */
 int ntg_synth_fastq_device(ntg_ctx* ctx, uint64_t dptr, uint64_t seed, uint64_t rec0, uint64_t nrec,

@@ -108,6 +108,7 @@ def load_library():
         "ntg_event_elapsed_ms": ([vp, C.c_int, C.c_int, P(C.c_float)], C.c_int),
         "ntg_parse_fastx": ([vp, vp, sz, P(P(_Records))], C.c_int),
         "ntg_records_free": ([P(_Records)], None),
+        "ntg_write_records": ([vp, vp, sz, C.c_int, vp, sz, vp, C.c_int, vp, sz, P(sz)], C.c_int),
         "ntg_parse_fastx_chunk": ([vp, vp, sz, C.c_int, C.c_int, P(P(_Records)), P(u64)], C.c_int),
         "ntg_stream_open": ([vp, P(_TallyConfig), P(vp)], C.c_int),
         "ntg_stream_feed": ([vp, vp, sz], C.c_int),
@@ -116,6 +117,16 @@ def load_library():
         "ntg_stream_feed_gz": ([vp, vp, sz, C.c_int], C.c_int),
         "ntg_stream_finish": ([vp, P(_Tallies), P(_ParseError)], C.c_int),
         "ntg_inflate_bgzf": ([vp, vp, sz, vp, sz, P(sz)], C.c_int),
+        "ntg_spectrum_create": ([vp, u32, u64, P(vp)], C.c_int),
+        "ntg_spectrum_destroy": ([vp], None),
+        "ntg_spectrum_clear": ([vp], C.c_int),
+        "ntg_spectrum_add_fastx": ([vp, vp, sz, P(_Tallies), P(_ParseError)], C.c_int),
+        "ntg_spectrum_add_fastx_device": ([vp, u64, sz, P(_Tallies), P(_ParseError)], C.c_int),
+        "ntg_spectrum_count": ([vp, cp, P(u64)], C.c_int),
+        "ntg_spectrum_export": ([vp, vp, vp, u64, P(u64)], C.c_int),
+        "ntg_spectrum_histogram": ([vp, vp, u32], C.c_int),
+        "ntg_spectrum_reduce": ([vp], C.c_int),
+        "ntg_spectrum_kmers": ([vp], u64),
         "ntg_stream_bytes": ([vp], u64),
         "ntg_stream_close": ([vp], None),
         "ntg_tally_fastx_file": ([vp, cp, P(_TallyConfig), C.c_int, P(_Tallies), P(_ParseError)], C.c_int),
@@ -260,6 +271,24 @@ class Context:
             return Parsed(arr, out.contents)
         finally:
             self.lib.ntg_records_free(out)
+
+    def write_records(self, data, parsed, keep=None, line_ending=None):
+        """Text of the kept records of a Parsed table (filtered output) — ntg_write_records; line_ending "unix" / "windows"
+        (default: the input's, like SequenceRecord::write)."""
+        arr = _as_u8(data)
+        table = np.ascontiguousarray(parsed.table, dtype=np.uint64)
+        le = {"unix": 1, "windows": 2, None: {"windows": 2}.get(parsed.line_ending, 1)}[line_ending]
+        fmt = {"fasta": 1, "fastq": 2}[parsed.format]
+        kp = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        assert kp is None or kp.size == len(table)
+        n = C.c_size_t()
+        args = (self.h, _ptr(arr), arr.size, fmt, table.ctypes.data if len(table) else None, len(table), kp.ctypes.data if kp is not None and kp.size else None, le)
+        st = self.lib.ntg_write_records(*args, None, 0, C.byref(n))
+        if st not in (OK, 16):
+            self._ck(st)
+        out = np.empty(max(1, n.value), dtype=np.uint8)
+        self._ck(self.lib.ntg_write_records(*args, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].tobytes()
 
     def parse_chunks(self, data, window=1 << 30):
         """Generator of Parsed, one per window of `window` bytes (< 4 GiB) — ntg_parse_fastx_chunk: the incremental reader behind
@@ -441,6 +470,9 @@ class Context:
         self._ck(self.lib.ntg_inflate_bgzf(self.h, _ptr(arr), arr.size, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value].tobytes()
 
+    def spectrum(self, k, capacity=0):
+        return Spectrum(self, k, capacity)
+
     def stream(self, k, m=0, iupac=False, query=None):
         """A tally session over a stream of unknown length (parse_fastx_reader<R: Read>) — ntg_stream_*"""
         return TallyStream(self, self._cfg(k, m, iupac, query))
@@ -478,6 +510,58 @@ class Context:
             setattr(t, f, d[f])
         self._ck(self.lib.ntg_comm_allreduce_tallies(self.h, C.byref(t)))
         return {f: int(getattr(t, f)) for f in TALLY_FIELDS}
+
+
+class Spectrum:
+    """ntg_spectrum: counts per distinct canonical k-mer (dense histogram for k <= 14, hash table of `capacity` slots above)."""
+
+    def __init__(self, ctx, k, capacity=0):
+        self.ctx, self.k, self.h = ctx, k, C.c_void_p()
+        ctx._ck(ctx.lib.ntg_spectrum_create(ctx.h, k, capacity, C.byref(self.h)))
+
+    def add(self, data):
+        arr = _as_u8(data); t = _Tallies(); e = _ParseError()
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_add_fastx(self.h, _ptr(arr), arr.size, C.byref(t), C.byref(e)))
+        return self.ctx._tally_result(t, e)
+
+    def add_device(self, dptr, nbytes):
+        t = _Tallies(); e = _ParseError()
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_add_fastx_device(self.h, dptr, nbytes, C.byref(t), C.byref(e)))
+        return self.ctx._tally_result(t, e)
+
+    def count(self, kmer):
+        v = C.c_uint64()
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_count(self.h, bytes(kmer), C.byref(v)))
+        return int(v.value)
+
+    def items(self):
+        """-> (keys uint64, counts uint32) of the distinct k-mers, sorted by key"""
+        n = C.c_uint64()
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_export(self.h, None, None, 0, C.byref(n)))
+        keys = np.empty(max(1, n.value), np.uint64); counts = np.empty(max(1, n.value), np.uint32)
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_export(self.h, keys.ctypes.data, counts.ctypes.data, n.value, C.byref(n)))
+        keys, counts = keys[:n.value], counts[:n.value]
+        o = np.argsort(keys, kind="stable")
+        return keys[o], counts[o]
+
+    def histogram(self, n_bins=256):
+        h = np.zeros(n_bins, np.uint64)
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_histogram(self.h, h.ctypes.data, n_bins))
+        return h
+
+    def reduce(self):
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_reduce(self.h))
+
+    def kmers_added(self):
+        return int(self.ctx.lib.ntg_spectrum_kmers(self.h))
+
+    def clear(self):
+        self.ctx._ck(self.ctx.lib.ntg_spectrum_clear(self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ntg_spectrum_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class TallyStream:
@@ -716,6 +800,18 @@ def normalize_seq(seq, iupac=False, ctx=None):
 def reverse_complement(seq, ctx=None):
     out = (ctx or default_context()).reverse_complement([seq.encode() if isinstance(seq, str) else seq])
     return out[0].decode()
+
+
+def write_fasta(id, seq, line_ending="unix"):
+    """record::write_fasta (src/parser/record.rs:207-220) as bytes: host formatting of ONE record (batches: Context.write_records)"""
+    e = b"\r\n" if line_ending == "windows" else b"\n"
+    return b">" + bytes(id) + e + bytes(seq) + e
+
+
+def write_fastq(id, seq, qual=None, line_ending="unix"):
+    """record::write_fastq (src/parser/record.rs:222-247): a missing quality is written as 'I' per base"""
+    e = b"\r\n" if line_ending == "windows" else b"\n"
+    return b"@" + bytes(id) + e + bytes(seq) + e + b"+" + e + (bytes(qual) if qual is not None else b"I" * len(seq)) + e
 
 
 def decode_phred(qual, base_64=False):

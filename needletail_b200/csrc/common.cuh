@@ -23,6 +23,7 @@ struct ntg_ctx {
     struct FusedState* fused = nullptr;
     // NCCL (nccl_dyn.cpp)
     void* nccl_comm = nullptr;
+    int nccl_ranks = 1, nccl_rank = 0;
     void* nccl_buf = nullptr;             // device staging for the tallies all-reduce
 };
 

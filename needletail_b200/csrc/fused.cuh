@@ -108,6 +108,13 @@ struct Params {
     unsigned long long* fin;           // k_finalize: [0] error kind of an end-of-stream error, [1] its line (FASTA)
     unsigned long long* reduce_buf;    // non-null: k_finalize copies the tallies (+ a "needs the host" count) into the all-reduce send buffer
     SState* final_state;
+    // k-mer spectrum passes (spectrum.cuh): every canonical k-mer the generic walker tallies is also counted, in a dense
+    // histogram (k <= 14: 4^k counters) or in an open-addressing hash table (keys ~0 = empty)
+    uint32_t* sp_dense;
+    unsigned long long* sp_keys;
+    uint32_t* sp_counts;
+    uint64_t sp_mask;
+    uint32_t* sp_overflow;
     uint32_t k, m, w;
     uint32_t tile_bytes;               // multiple of 256, <= TILE: sized so one tile holds about NT sequence lines
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
@@ -266,6 +273,23 @@ __host__ __device__ __forceinline__ void scan_row(const uint32_t* __restrict__ r
     mask = rot ? ((m << rot) | (m >> (64u - rot))) : m;
 }
 
+// ---- k-mer spectrum: count one canonical k-mer (k <= 32) ----------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t h) {          // MurmurHash3 finaliser
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h;
+}
+constexpr uint32_t SPECTRUM_MAX_PROBES = 8192;
+__device__ __forceinline__ void spectrum_add(unsigned long long* keys, uint32_t* counts, uint64_t mask, uint32_t* overflow, uint64_t key, uint32_t inc) {
+    uint64_t h = fmix64(key) & mask;
+    for (uint32_t probe = 0; probe < SPECTRUM_MAX_PROBES; probe++) {
+        unsigned long long old = keys[h];
+        if (old == ~0ull) old = atomicCAS(&keys[h], ~0ull, (unsigned long long)key);
+        if (old == ~0ull || old == key) { atomicAdd(&counts[h], inc); return; }
+        h = (h + 1) & mask;
+    }
+    atomicAdd(overflow, 1u);                                               // table full: the host reports NTG_ENOMEM
+}
+
 // =============================================================================== the walker
 // Processes the sequence bytes sb[a..b) (tile-relative; sb[-HALO..-1] is the back halo) of one
 // sequence-line fragment.  `lo` = lowest index the warm-up may read; lo_exact tells whether lo is the
@@ -364,6 +388,12 @@ __host__ __device__ __forceinline__ void walk(const uint8_t* __restrict__ sb, co
                 acc.ksum_lo += c0;
                 if (KW == 2) acc.ksum_hi += c1;
                 if (P.has_query && c0 == P.q_lo && (KW == 1 || c1 == P.q_hi)) acc.n_query++;
+#ifdef __CUDA_ARCH__
+                if (KW == 1 && !MINI) {
+                    if (P.sp_dense) atomicAdd(&P.sp_dense[c0], 1u);
+                    else if (P.sp_keys) spectrum_add(P.sp_keys, P.sp_counts, P.sp_mask, P.sp_overflow, c0, 1u);
+                }
+#endif
                 if (MINI) { acc.n_mini++; acc.msum += win; }
             }
         }

@@ -69,6 +69,8 @@ struct FusedState {
     // sniff cache of the resident entry point: (pointer, size) -> format + tile size, verified on the device (byte 0)
     uint64_t sniff_ptr = 0; size_t sniff_n = 0; int sniff_format = 0; uint32_t sniff_tile = 0;
     uint64_t pend_dptr = 0; size_t pend_n = 0;
+    // spectrum binding of the passes to come (spectrum.cuh sets and clears it)
+    uint32_t* sp_dense = nullptr; unsigned long long* sp_keys = nullptr; uint32_t* sp_counts = nullptr; uint64_t sp_mask = 0; uint32_t* sp_overflow = nullptr;
 };
 
 typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64_t, const uint32_t, uint32_t*);
@@ -79,7 +81,7 @@ typedef void (*fused_kernel_t)(const fused::Params, const uint64_t, const uint64
     X((k_fused<2, false, 0, 51, 0>))
 static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) {
     using namespace fused;
-    if (has_query) {                           // the query count lives in the generic walkers only
+    if (has_query) {                           // (spectrum passes come here too: the generic walker is the one that counts)                           // the query count lives in the generic walkers only
         if (k > 32) return k_fused<2, false, 0, 0, 0>;
         if (m == 0) return k_fused<1, false, 0, 0, 0>;
         return (k - m + 1 == 11) ? k_fused<1, true, 11, 0, 0> : k_fused<1, true, 0, 0, 0>;
@@ -198,6 +200,7 @@ static int fused_begin_pass(ntg_ctx* ctx, int format, const ntg_tally_config* cf
             P.q_hi = (P.q_hi << 2) | (P.q_lo >> 62);
             P.q_lo = (P.q_lo << 2) | host_luts().code[cfg->query[i]];
         }
+    P.sp_dense = st->sp_dense; P.sp_keys = st->sp_keys; P.sp_counts = st->sp_counts; P.sp_mask = st->sp_mask; P.sp_overflow = st->sp_overflow;
     st->cfg = *cfg; st->format = format; st->general_tile_bytes = tile_bytes;
     return NTG_OK;
 }
@@ -219,7 +222,7 @@ static int fused_enqueue_launch(ntg_ctx* ctx, const uint8_t* base, uint64_t gmin
     if (te > tb) {
         const uint64_t nt = te - tb;
         const unsigned grid = (unsigned)(nt < (uint64_t)st->max_ctas ? nt : (uint64_t)st->max_ctas);
-        fused_kernel_t kf = pick_fused_kernel(P.k, P.m, P.has_query != 0);
+        fused_kernel_t kf = pick_fused_kernel(P.k, P.m, P.has_query != 0 || P.sp_dense || P.sp_keys);
         kf<<<grid, fused::NT, sizeof(fused::Smem), ctx->stream>>>(P, tb, te, st->epoch, &c->ticket);
         ctx->launches++;
         NTG_CUDA(ctx, cudaGetLastError());

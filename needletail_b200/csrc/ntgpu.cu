@@ -55,6 +55,8 @@ static bool load() {
 }
 }  // namespace nccldyn
 
+#include "spectrum.cuh"
+
 extern "C" {
 
 int ntg_abi_version(void) { return NTG_ABI_VERSION; }
@@ -170,6 +172,11 @@ int ntg_event_elapsed_ms(ntg_ctx* ctx, int a, int b, float* ms) {
 int ntg_parse_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, ntg_records** out) {
     CTX_ENTER(ctx);
     return run_parse_device(ctx, bytes, nullptr, n, out, nullptr);
+}
+int ntg_write_records(ntg_ctx* ctx, const uint8_t* bytes, size_t n, int format, const ntg_record* records, size_t n_records, const uint8_t* keep,
+                      int line_ending, uint8_t* out, size_t out_cap, size_t* out_len) {
+    CTX_ENTER(ctx);
+    return run_write_records(ctx, bytes, n, format, records, n_records, keep, line_ending, out, out_cap, out_len);
 }
 void ntg_records_free(ntg_records* r) {
     if (!r) return;
@@ -520,6 +527,98 @@ int ntg_parse_fastx_chunk(ntg_ctx* ctx, const uint8_t* bytes, size_t n, int form
     return run_parse_device(ctx, bytes, nullptr, n, out, nullptr, format, at_eof != 0, consumed, nullptr);
 }
 
+// ---- (3c) k-mer spectrum ------------------------------------------------------------------------
+#define SPECTRUM_ENTER(sp)                                                   \
+    if (!(sp) || !(sp)->ctx) return NTG_EINVAL;                              \
+    if (cudaSetDevice((sp)->ctx->device) != cudaSuccess) return ntg_set_error((sp)->ctx, NTG_ECUDA, "cudaSetDevice failed")
+int ntg_spectrum_create(ntg_ctx* ctx, uint32_t k, uint64_t capacity, ntg_spectrum** out) {
+    CTX_ENTER(ctx);
+    return spectrum_create(ctx, k, capacity, out);
+}
+void ntg_spectrum_destroy(ntg_spectrum* sp) { spectrum_free(sp); }
+int ntg_spectrum_clear(ntg_spectrum* sp) { SPECTRUM_ENTER(sp); return spectrum_clear(sp); }
+static ntg_tally_config spectrum_cfg(const ntg_spectrum* sp) { ntg_tally_config c; std::memset(&c, 0, sizeof(c)); c.k = sp->k; return c; }
+int ntg_spectrum_add_fastx_device(ntg_spectrum* sp, uint64_t dptr, size_t n, ntg_tallies* tallies, ntg_parse_error* err) {
+    SPECTRUM_ENTER(sp);
+    ntg_ctx* ctx = sp->ctx;
+    if (n < 2 || !dptr || (dptr & 15)) return ntg_set_error(ctx, NTG_EINVAL, "spectrum: >= 2 device-resident bytes at a 16-byte aligned address");
+    int format; uint32_t tile_bytes;
+    NTG_TRY(resident_sniff(ctx, dptr, n, false, &format, &tile_bytes));
+    const ntg_tally_config cfg = spectrum_cfg(sp);
+    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_resident(ctx, (const uint8_t*)(uintptr_t)dptr, n_eff, format, &cfg, tile_bytes, spec, r); };
+    return spectrum_add_input(sp, n, format, run, tallies, err);
+}
+int ntg_spectrum_add_fastx(ntg_spectrum* sp, const uint8_t* bytes, size_t n, ntg_tallies* tallies, ntg_parse_error* err) {
+    SPECTRUM_ENTER(sp);
+    ntg_ctx* ctx = sp->ctx;
+    if (n && !bytes) return ntg_set_error(ctx, NTG_EINVAL, "null input");
+    int format;
+    ntg_tallies scratch;
+    if (sniff_format(ctx, n ? bytes[0] : 0, n, tallies ? tallies : &scratch, err, &format)) return NTG_OK;
+    const uint32_t tile_bytes = pick_tile_bytes(bytes, n < 65536 ? n : 65536, format);
+    const ntg_tally_config cfg = spectrum_cfg(sp);
+    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_host(ctx, bytes, n_eff, format, &cfg, tile_bytes, spec, r); };
+    return spectrum_add_input(sp, n, format, run, tallies, err);
+}
+int ntg_spectrum_count(ntg_spectrum* sp, const uint8_t* kmer, uint64_t* count) {
+    SPECTRUM_ENTER(sp);
+    ntg_ctx* ctx = sp->ctx;
+    if (!kmer || !count) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
+    uint64_t f = 0, r = 0;
+    for (uint32_t i = 0; i < sp->k; i++) {
+        const uint8_t c = host_luts().code[kmer[i]];
+        if (c > 3) return ntg_set_error(ctx, NTG_EINVAL, "k-mer must be k bases of ACGT");
+        f = (f << 2) | c;
+        r = (r >> 2) | ((uint64_t)(3 - c) << (2 * (sp->k - 1)));
+    }
+    const uint64_t key = f < r ? f : r;
+    uint32_t v = 0;
+    if (sp->dense) NTG_CUDA(ctx, cudaMemcpyAsync(&v, sp->d_dense + key, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    else {
+        spectrum::k_lookup<<<1, 1, 0, ctx->stream>>>(sp->d_keys, sp->d_counts, sp->capacity - 1, key, sp->d_overflow + 1);
+        ctx->launches++;
+        NTG_CUDA(ctx, cudaMemcpyAsync(&v, sp->d_overflow + 1, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *count = v;
+    return NTG_OK;
+}
+int ntg_spectrum_export(ntg_spectrum* sp, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_distinct) {
+    SPECTRUM_ENTER(sp);
+    ntg_ctx* ctx = sp->ctx;
+    if (!n_distinct || (cap && (!keys || !counts))) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
+    DevBuf<unsigned long long> dk, cur; DevBuf<uint32_t> dc;
+    if (dk.alloc(cap) || dc.alloc(cap) || cur.alloc(1)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    NTG_CUDA(ctx, cudaMemsetAsync(cur.p, 0, 8, ctx->stream));
+    spectrum::k_export<<<spectrum::grid_for(sp->capacity, ctx->sm_count), spectrum::BLOCK, 0, ctx->stream>>>(sp->d_dense, sp->d_keys, sp->d_counts, sp->capacity, dk.p, dc.p, cap, cur.p);
+    ctx->launches++;
+    unsigned long long nd = 0;
+    NTG_CUDA(ctx, cudaMemcpyAsync(&nd, cur.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_distinct = nd;
+    const uint64_t take = nd < cap ? nd : cap;
+    if (take) {
+        NTG_CUDA(ctx, cudaMemcpy(keys, dk.p, take * 8, cudaMemcpyDeviceToHost));
+        NTG_CUDA(ctx, cudaMemcpy(counts, dc.p, take * 4, cudaMemcpyDeviceToHost));
+    }
+    return NTG_OK;
+}
+int ntg_spectrum_histogram(ntg_spectrum* sp, uint64_t* hist, uint32_t n_bins) {
+    SPECTRUM_ENTER(sp);
+    ntg_ctx* ctx = sp->ctx;
+    if (!hist || n_bins < 2) return ntg_set_error(ctx, NTG_EINVAL, "histogram needs >= 2 bins");
+    DevBuf<unsigned long long> dh;
+    if (dh.alloc(n_bins)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    NTG_CUDA(ctx, cudaMemsetAsync(dh.p, 0, (size_t)n_bins * 8, ctx->stream));
+    spectrum::k_count_hist<<<spectrum::grid_for(sp->capacity, ctx->sm_count), spectrum::BLOCK, 0, ctx->stream>>>(sp->d_dense, sp->d_keys, sp->d_counts, sp->capacity, dh.p, n_bins);
+    ctx->launches++;
+    NTG_CUDA(ctx, cudaMemcpyAsync(hist, dh.p, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NTG_OK;
+}
+int ntg_spectrum_reduce(ntg_spectrum* sp) { SPECTRUM_ENTER(sp); return spectrum_reduce(sp); }
+uint64_t ntg_spectrum_kmers(const ntg_spectrum* sp) { return sp ? sp->n_added : 0; }
+
 // ---- (4) synthetic inputs ----------------------------------------------------------------------
 int ntg_synth_fastq_device(ntg_ctx* ctx, uint64_t dptr, uint64_t seed, uint64_t rec0, uint64_t nrec, uint32_t read_len, uint32_t n_thresh) {
     CTX_ENTER(ctx);
@@ -548,6 +647,7 @@ int ntg_comm_init(ntg_ctx* ctx, int n_ranks, int rank, const uint8_t id[NTG_NCCL
     std::memcpy(u.internal, id, NTG_NCCL_ID_BYTES);
     int r = nccldyn::CommInitRank(&ctx->nccl_comm, n_ranks, u, rank);
     if (r != 0) { ctx->nccl_comm = nullptr; return ntg_set_error(ctx, NTG_ENCCL, "ncclCommInitRank: %s", nccldyn::GetErrorString(r)); }
+    ctx->nccl_ranks = n_ranks; ctx->nccl_rank = rank;
     NTG_CUDA(ctx, cudaMalloc(&ctx->nccl_buf, sizeof(ntg_tallies)));
     return NTG_OK;
 }

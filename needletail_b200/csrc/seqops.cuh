@@ -139,6 +139,36 @@ __global__ void __launch_bounds__(BLOCK) k_kmer_emit(const uint8_t* __restrict__
     }
 }
 
+// ---- record writers: write_fasta / write_fastq (src/parser/record.rs:207-247) for a batch of kept records ------------------
+// One warp per record: '>' / '@', id, line ending, raw_seq, line ending [, '+', line ending, qual (or 'I' x seq length when the
+// record has none), line ending].  `src` holds the text the record table indexes; `dst_off[r]` is where record r's text starts.
+struct WriteRow { uint64_t id_b, id_e, seq_b, seq_e, qual_b, qual_e, dst; uint32_t fastq, has_qual; };
+__global__ void __launch_bounds__(BLOCK) k_write_records(const uint8_t* __restrict__ src, const WriteRow* __restrict__ rows, uint32_t n_rows,
+                                                         uint32_t le_len, uint8_t* __restrict__ dst) {
+    const uint32_t w = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const WriteRow r = rows[w];
+    const uint64_t idl = r.id_e - r.id_b, sl = r.seq_e - r.seq_b, ql = r.fastq ? (r.has_qual ? r.qual_e - r.qual_b : sl) : 0;
+    // segments of the output: [0] start byte, [1] id, [2] ending, [3] seq, [4] ending, (fastq) [5] '+', [6] ending, [7] qual, [8] ending
+    const uint64_t e1 = 1 + idl, e2 = e1 + le_len, e3 = e2 + sl, e4 = e3 + le_len;
+    const uint64_t e5 = e4 + (r.fastq ? 1 : 0), e6 = e5 + (r.fastq ? le_len : 0), e7 = e6 + ql, e8 = e7 + (r.fastq ? le_len : 0);
+    auto ending = [&](uint64_t k) -> uint8_t { return (le_len == 2 && k == 0) ? (uint8_t)'\r' : (uint8_t)'\n'; };
+    uint8_t* o = dst + r.dst;
+    for (uint64_t p = lane; p < e8; p += 32) {
+        uint8_t b;
+        if (p == 0) b = r.fastq ? '@' : '>';
+        else if (p < e1) b = src[r.id_b + (p - 1)];
+        else if (p < e2) b = ending(p - e1);
+        else if (p < e3) b = src[r.seq_b + (p - e2)];
+        else if (p < e4) b = ending(p - e3);
+        else if (p < e5) b = '+';
+        else if (p < e6) b = ending(p - e5);
+        else if (p < e7) b = r.has_qual ? src[r.qual_b + (p - e6)] : (uint8_t)'I';
+        else b = ending(p - e7);
+        o[p] = b;
+    }
+}
+
 // ---- element-wise BitKmer helpers -------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_bitkmer_elem(const uint64_t* __restrict__ in, size_t n, uint32_t k, uint32_t m, int mode,
                                                         uint64_t* __restrict__ out, uint8_t* __restrict__ was_rc) {
@@ -357,6 +387,43 @@ static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const
     it->val_lo = want_val ? priv->val_lo.p : nullptr; it->val_hi = want_hi ? priv->val_hi.p : nullptr;
     it->_priv = priv;
     *out = it;
+    return NTG_OK;
+}
+
+// Text of the kept records of a record table, in table order.  keep == nullptr: all.  line_ending: NTG_LE_UNIX / NTG_LE_WINDOWS.
+static int run_write_records(ntg_ctx* ctx, const uint8_t* bytes, size_t n, int format, const ntg_record* recs, size_t n_recs, const uint8_t* keep,
+                             int line_ending, uint8_t* out, size_t out_cap, size_t* out_len) {
+    using namespace seqops;
+    if (!out_len || (n_recs && !recs) || (n && !bytes)) return ntg_set_error(ctx, NTG_EINVAL, "null pointer");
+    if (format != NTG_FMT_FASTA && format != NTG_FMT_FASTQ) return ntg_set_error(ctx, NTG_EINVAL, "format must be FASTA or FASTQ");
+    if (line_ending != NTG_LE_UNIX && line_ending != NTG_LE_WINDOWS) return ntg_set_error(ctx, NTG_EINVAL, "line ending must be unix or windows");
+    const uint32_t le = line_ending == NTG_LE_WINDOWS ? 2 : 1;
+    const bool fq = format == NTG_FMT_FASTQ;
+    std::vector<WriteRow> rows;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_recs; i++) {
+        if (keep && !keep[i]) continue;
+        const ntg_record& r = recs[i];
+        if (r.id_e > n || r.seq_e > n || (fq && r.qual_e > n) || r.id_b > r.id_e || r.seq_b > r.seq_e) return ntg_set_error(ctx, NTG_EINVAL, "record %zu points outside the buffer", i);
+        const uint64_t sl = r.seq_e - r.seq_b;
+        rows.push_back(WriteRow{r.id_b, r.id_e, r.seq_b, r.seq_e, r.qual_b, r.qual_e, total, fq ? 1u : 0u, 1u});
+        total += 1 + (r.id_e - r.id_b) + le + sl + le + (fq ? 1 + le + (r.qual_e - r.qual_b) + le : 0);
+    }
+    *out_len = (size_t)total;
+    if (total > out_cap) return ntg_set_error(ctx, NTG_EINVAL, "output buffer too small: %llu bytes needed", (unsigned long long)total);
+    if (rows.empty()) return NTG_OK;
+    if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output");
+    if (rows.size() >= 0x07FFFFFFull) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "write at most 2^27 records per call");
+    DevBuf<uint8_t> dsrc, ddst; DevBuf<WriteRow> drows;
+    if (dsrc.alloc(n) || ddst.alloc(total) || drows.alloc(rows.size())) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+    NTG_CUDA(ctx, cudaMemcpyAsync(dsrc.p, bytes, n, cudaMemcpyHostToDevice, ctx->stream));
+    NTG_CUDA(ctx, cudaMemcpyAsync(drows.p, rows.data(), rows.size() * sizeof(WriteRow), cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t threads = (uint64_t)rows.size() * 32;
+    k_write_records<<<(unsigned)((threads + BLOCK - 1) / BLOCK), BLOCK, 0, ctx->stream>>>(dsrc.p, drows.p, (uint32_t)rows.size(), le, ddst.p);
+    ctx->launches++;
+    NTG_CUDA(ctx, cudaGetLastError());
+    NTG_CUDA(ctx, cudaMemcpyAsync(out, ddst.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NTG_OK;
 }
 

@@ -446,3 +446,33 @@ def test_non_speculative_path_agrees(ctx):
                     assert all(t[key] == e[key] for key in e), (flags, k, m, {key: (t[key], e[key]) for key in e if t[key] != e[key]})
     finally:
         ctx.tally_flags = 0
+
+
+def test_record_writers(ctx, fixtures):  # src/parser/record.rs:158-247, tests at record.rs:258-293
+    import needletail_b200 as nt
+    assert nt.write_fasta(b"id", b"ACGT") == b">id\nACGT\n" and nt.write_fasta(b"id", b"ACGT", "windows") == b">id\r\nACGT\r\n"
+    assert nt.write_fastq(b"id", b"ACGT", None) == b"@id\nACGT\n+\nIIII\n" and nt.write_fastq(b"i", b"AC", b"!!", "windows") == b"@i\r\nAC\r\n+\r\n!!\r\n"
+    rng = random.Random(41)
+    for name in ("data/PRJNA271013_head.fq", "data/28S.fasta", "data/test.fa"):
+        data = fixtures[name]
+        p = ctx.parse(data)
+        n = len(p.records)
+        for le in (None, "unix", "windows"):
+            keep = np.array([rng.random() < 0.6 for _ in range(n)], dtype=np.uint8)
+            for kp in (None, keep, np.zeros(n, np.uint8)):
+                eol = b"\r\n" if (le == "windows" or (le is None and p.line_ending == "windows")) else b"\n"
+                want = []
+                for i, r in enumerate(p.records):
+                    if kp is not None and not kp[i]:
+                        continue
+                    idb = data[int(p.table[i, 1]):int(p.table[i, 2])]
+                    if p.format == "fasta":
+                        want.append(b">" + idb + eol + r.raw_seq + eol)
+                    else:
+                        want.append(b"@" + idb + eol + r.raw_seq + eol + b"+" + eol + r.qual.encode() + eol)
+                assert ctx.write_records(data, p, kp, le) == b"".join(want), (name, le)
+    # a FASTQ written back unfiltered with its own line ending parses to the same table of sequences
+    fq = fixtures["data/PRJNA271013_head.fq"]
+    p = ctx.parse(fq)
+    back = ctx.parse(ctx.write_records(fq, p))
+    assert [r.seq for r in back.records] == [r.seq for r in p.records] and [r.qual for r in back.records] == [r.qual for r in p.records]
