@@ -17,6 +17,7 @@ CONFIGS = [
     ("C4 100M x 150bp FASTQ 1% N k=31 m=21 (one GPU's shard)", "fastq", 100_000_000, 150, 31, 21, 655, 0x5EED0004),
     ("C3 shape, 4M x 10kbp FASTA k=21 m=11 (40 of the 100 Gbases)", "fasta", 4_000_000, 10_000, 21, 11, 0, 0x5EED0003),
     ("C5 shape, 50M x 250bp FASTQ k=51 (text resident; gzip inflate is host work)", "fastq", 50_000_000, 250, 51, 0, 0, 0x5EED0005),
+    ("C3 10M x 10kbp FASTA k=21 m=11 (the named size: 100 GB of text resident in HBM)", "fasta", 10_000_000, 10_000, 21, 11, 0, 0x5EED0003),
     # not a BASELINE config: the same FASTA shape wrapped at 70 columns (what genome FASTA files look like); generated on the host
     ("C3w 120k x 10kbp FASTA wrapped at 70 columns, k=21 m=11 (host-generated, 1.2 GB)", "fasta_wrapped", 120_000, 10_000, 21, 11, 0, 0x5EED0013),
 ]
