@@ -216,6 +216,8 @@ typedef struct ntg_tally_config {
  * collect returns that rank's LOCAL tallies with NTG_RESERVED_NOT_REDUCED set in reserved[0]: reduce them with
  * ntg_comm_allreduce_tallies. */
 #define NTG_TALLY_ALLREDUCE 2u
+/* diagnostic: short-read FASTQ goes through the general tile kernel (fused::k_fused) instead of the record-owned fast path */
+#define NTG_TALLY_NO_FASTPATH 4u
 #define NTG_RESERVED_NOT_REDUCED (1ull << 32)
 
 typedef struct ntg_tallies {

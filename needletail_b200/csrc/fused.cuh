@@ -1529,6 +1529,15 @@ __global__ void k_finalize(const Params P) {
     }
 }
 
+// record-owned passes with NTG_TALLY_ALLREDUCE: tallies -> NCCL send buffer ([9] = this rank needs the host: flags, or a tail)
+__global__ void k_reduce_copy(const unsigned long long* tallies, const uint32_t* flags, const unsigned long long* next, uint64_t n_vis,
+                              unsigned long long* reduce_buf) {
+    const uint32_t i = threadIdx.x;
+    if (i < 9) reduce_buf[i] = tallies[i];
+    else if (i == 9) reduce_buf[9] = (*flags || *next < n_vis) ? 1ull : 0ull;
+    else if (i < 16) reduce_buf[i] = 0;
+}
+
 // ---- exact fallback: one thread per parsed record walks its raw_seq from global memory ---------
 template <int KW, bool MINI>
 __global__ void __launch_bounds__(128) k_tally_records(const Params P, const ntg_record* __restrict__ recs, uint64_t n_recs) {

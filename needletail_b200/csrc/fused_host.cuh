@@ -14,6 +14,7 @@
 #include <functional>
 
 #include "fused.cuh"
+#include "fastq_warp.cuh"
 #include "parse.cuh"
 
 struct LaunchCtl {                    // device-resident control block of one launch (mirrored in pinned host memory)
@@ -31,15 +32,20 @@ constexpr size_t STREAM_BACK = size_t(1) << 20;      // bytes of history kept in
 constexpr size_t STREAM_SEG = size_t(64) << 20;      // segment size of streamed passes (rounded down to whole tiles)
 constexpr int NSEG = 3;                              // device segments: a flagged launch and its neighbours stay intact until checked
 
+// launch shape of a pass, chosen from the first bytes of the input: tile size of fused::k_fused; chunk size and fragments per
+// sequence line of the record-owned fast path when the input is short-read FASTQ
+struct PassShape { uint32_t tile_bytes = 0; bool fq_ok = false; uint32_t cb = 0, frags = 1; };
+
 struct PassResult {                   // sum over the launches of one pass
     unsigned long long tallies[16] = {};
     unsigned long long err_key = ~0ull;
     unsigned long long fin[4] = {};
     uint32_t flags = 0;
+    uint64_t fq_next = ~0ull;             // record-owned passes: where the first record that was not complete begins (the tail)
     void add(const LaunchCtl& c) {
         for (int i = 0; i < 16; i++) tallies[i] += c.tallies[i];
         if (c.err_key < err_key) err_key = c.err_key;
-        if (c.fin[0]) for (int i = 0; i < 4; i++) fin[i] = c.fin[i];
+        if (c.fin[0]) for (int i = 0; i < 3; i++) fin[i] = c.fin[i];
         flags |= c.flags;
     }
 };
@@ -61,14 +67,21 @@ struct FusedState {
     unsigned long long* reduce_buf = nullptr;   // 16 x u64: send/receive buffer of the in-stream tallies all-reduce
     unsigned long long* h_reduce = nullptr;     // pinned mirror
     // resident call pending between enqueue and collect
-    bool pending = false, pending_reduce = false;
+    bool pending = false, pending_reduce = false, pending_fq = false;
     fused::Params P{};
     ntg_tally_config cfg{};
     int format = 0;
     uint32_t general_tile_bytes = 0;
     // sniff cache of the resident entry point: (pointer, size) -> format + tile size, verified on the device (byte 0)
-    uint64_t sniff_ptr = 0; size_t sniff_n = 0; int sniff_format = 0; uint32_t sniff_tile = 0;
+    uint64_t sniff_ptr = 0; size_t sniff_n = 0; int sniff_format = 0; uint32_t sniff_flags = 0; PassShape sniff_shape;
     uint64_t pend_dptr = 0; size_t pend_n = 0;
+    // record-owned FASTQ fast path (fastq_warp.cuh)
+    int fq_max_ctas = 0;
+    uint8_t* fq_info = nullptr; size_t fq_info_cap = 0;        // per-chunk bytes of the launch in flight (ring of NCTL regions)
+    uint32_t* fq_fix_list = nullptr; uint8_t* fq_fix_phase = nullptr;
+    unsigned long long* fq_words = nullptr;                    // [0, NCTL): start word per launch slot; [NCTL, 2 NCTL): carry words
+    uint32_t* fq_counters = nullptr;                           // per slot: ticket, fix ticket, fix count, pad
+    bool fq_disable = false;                                   // NTG_TALLY_NO_FASTPATH
     // spectrum binding of the passes to come (spectrum.cuh sets and clears it)
     uint32_t* sp_dense = nullptr; unsigned long long* sp_keys = nullptr; uint32_t* sp_counts = nullptr; uint64_t sp_mask = 0; uint32_t* sp_overflow = nullptr;
 };
@@ -94,6 +107,70 @@ static fused_kernel_t pick_fused_kernel(uint32_t k, uint32_t m, bool has_query) 
     if (m == 0) return k_fused<1, false, 0, 0, 0>;
     if (k - m + 1 == 11) return k_fused<1, true, 11, 0, 0>;
     return k_fused<1, true, 0, 0, 0>;
+}
+
+// ---- record-owned FASTQ fast path: kernel table, launch-shape choice --------------------------------------------------
+typedef void (*fq_kernel_t)(const fqw::Params);
+#define NTG_FQ_KERNELS(X) \
+    X((k_records<1, true, 11, 31, 21>)) X((k_records<1, true, 11, 21, 11>)) X((k_records<1, false, 0, 31, 0>)) \
+    X((k_records<2, false, 0, 0, 0>)) X((k_records<1, false, 0, 0, 0>)) X((k_records<1, true, 11, 0, 0>)) X((k_records<1, true, 0, 0, 0>)) \
+    X((k_records<2, false, 0, 51, 0>))
+static fq_kernel_t pick_fq_kernel(uint32_t k, uint32_t m, bool generic) {
+    using namespace fqw;
+    if (generic) {
+        if (k > 32) return k_records<2, false, 0, 0, 0>;
+        if (m == 0) return k_records<1, false, 0, 0, 0>;
+        return (k - m + 1 == 11) ? k_records<1, true, 11, 0, 0> : k_records<1, true, 0, 0, 0>;
+    }
+    if (k == 51 && m == 0) return k_records<2, false, 0, 51, 0>;
+    if (k == 31 && m == 21) return k_records<1, true, 11, 31, 21>;
+    if (k == 21 && m == 11) return k_records<1, true, 11, 21, 11>;
+    if (k == 31 && m == 0) return k_records<1, false, 0, 31, 0>;
+    if (k > 32) return k_records<2, false, 0, 0, 0>;
+    if (m == 0) return k_records<1, false, 0, 0, 0>;
+    if (k - m + 1 == 11) return k_records<1, true, 11, 0, 0>;
+    return k_records<1, true, 0, 0, 0>;
+}
+constexpr uint32_t FQ_FIX_CAP = 1u << 16;
+constexpr size_t FQ_INFO_SLOT = size_t(1) << 24;            // chunk bytes per launch slot (16 Mi chunks = 160 GB of text)
+static int fq_init(ntg_ctx* ctx) {
+    FusedState* st = ctx->fused;
+    using namespace fqw;
+#define NTG_X(k) (fq_kernel_t)k,
+    fq_kernel_t ks[] = {NTG_FQ_KERNELS(NTG_X)};
+#undef NTG_X
+    int occ_min = 1 << 30;
+    for (auto kf : ks) {
+        NTG_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fqw::Smem)));
+        int occ = 0;
+        NTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, fqw::NT, sizeof(fqw::Smem)));
+        if (occ < 1) return ntg_set_error(ctx, NTG_ECUDA, "record-owned FASTQ kernel does not fit on an SM");
+        occ_min = occ < occ_min ? occ : occ_min;
+    }
+    st->fq_max_ctas = occ_min * ctx->sm_count;
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->fq_info, FQ_INFO_SLOT * 2));
+    st->fq_info_cap = FQ_INFO_SLOT;
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->fq_fix_list, FQ_FIX_CAP * sizeof(uint32_t)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->fq_fix_phase, FQ_FIX_CAP));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->fq_words, 2 * NCTL * sizeof(unsigned long long)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->fq_counters, 4 * NCTL * sizeof(uint32_t)));
+    return NTG_OK;
+}
+// Launch shape from the first bytes of a FASTQ stream: bytes per record -> fragments per sequence line and chunk size such
+// that a chunk holds about 31 items (one per lane).  false: not a short-read shape (records above 1.3 KB), use fused::k_fused.
+static bool fq_shape(const uint8_t* sample, size_t ns, uint32_t* cb, uint32_t* frags) {
+    size_t nl = 0;
+    for (size_t i = 0; i < ns; i++) nl += sample[i] == '\n';
+    if (nl < 8) return false;
+    const double rec = 4.0 * (double)ns / (double)nl;
+    uint32_t f = 1;
+    while (f <= 4 && rec * 31.0 / f > fqw::CBMAX) f *= 2;
+    if (f > 4 || rec * 2.5 > fqw::SLACK) return false;
+    uint32_t c = ((uint32_t)(rec * 31.0 / f) + 15u) & ~15u;
+    if (c < 1024u) c = 1024u;
+    if (c > (uint32_t)fqw::CBMAX) c = fqw::CBMAX;
+    *cb = c; *frags = f;
+    return true;
 }
 
 static int fused_init(ntg_ctx* ctx) {
@@ -126,6 +203,7 @@ static int fused_init(ntg_ctx* ctx) {
         occ_min = occ < occ_min ? occ : occ_min;
     }
     st->max_ctas = occ_min * ctx->sm_count;     // persistent grid: every CTA resident (look-back needs forward progress)
+    NTG_TRY(fq_init(ctx));
     return NTG_OK;
 }
 static void fused_destroy(ntg_ctx* ctx) {
@@ -133,6 +211,7 @@ static void fused_destroy(ntg_ctx* ctx) {
     if (!st) return;
     cudaFree(st->slots); cudaFree(st->cw); cudaFree(st->ctl); cudaFree(st->final_state); cudaFreeHost(st->h_ctl);
     cudaFree(st->reduce_buf); cudaFreeHost(st->h_reduce);
+    cudaFree(st->fq_info); cudaFree(st->fq_fix_list); cudaFree(st->fq_fix_phase); cudaFree(st->fq_words); cudaFree(st->fq_counters);
     for (auto& p : st->seg) cudaFree(p);
     if (st->ev_k0) cudaEventDestroy(st->ev_k0);
     if (st->ev_k1) cudaEventDestroy(st->ev_k1);
@@ -240,10 +319,75 @@ static int fused_enqueue_launch(ntg_ctx* ctx, const uint8_t* base, uint64_t gmin
     return NTG_OK;
 }
 
+// Enqueue one launch of the record-owned fast path: records starting at the device word fq_words[slot_in] (0 for the first
+// launch of a pass) and complete inside the first n_vis stream bytes.  k_verify leaves the start of the first record that was
+// not (the next launch's start) in fq_words[slot_out] and in ctl.fin[3].  `span` bounds the bytes the launch can cover.
+static int fq_enqueue_launch(ntg_ctx* ctx, const uint8_t* base, uint64_t n_vis, uint64_t span, uint32_t cb, uint32_t frags, uint64_t seq, bool final, int ci,
+                             bool reduce = false, bool keep_start = false) {
+    FusedState* st = ctx->fused;
+    LaunchCtl* c = st->ctl + ci;
+    const int wi = (int)(seq % NCTL), wo = (int)((seq + 1) % NCTL);
+    const bool first = seq == 0 && !keep_start;
+    NTG_CUDA(ctx, cudaMemsetAsync(c, 0, sizeof(LaunchCtl), ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(&c->err_key, 0xFF, sizeof(c->err_key), ctx->stream));
+    const uint64_t n_chunks_max = span / cb + 3;
+    if (n_chunks_max > st->fq_info_cap) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "launch too large for the record-owned path");
+    uint8_t* info = st->fq_info + (size_t)(seq & 1) * st->fq_info_cap;
+    NTG_CUDA(ctx, cudaMemsetAsync(info, 0, n_chunks_max, ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(st->fq_counters + 4 * wi, 0, 4 * sizeof(uint32_t), ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(st->fq_words + NCTL + wi, 0xFF, sizeof(unsigned long long), ctx->stream));
+    if (first) NTG_CUDA(ctx, cudaMemsetAsync(st->fq_words + wi, 0, sizeof(unsigned long long), ctx->stream));
+    fqw::Params P{};
+    P.W = st->P;
+    P.W.tallies = c->tallies; P.W.flags = &c->flags; P.W.err_key = &c->err_key; P.W.fin = c->fin;
+    P.bytes = base; P.start = st->fq_words + wi; P.n_vis = n_vis; P.cb = cb; P.frags = frags; P.info = info;
+    P.ticket = st->fq_counters + 4 * wi; P.carry = st->fq_words + NCTL + wi;
+    P.fix_list = nullptr; P.fix_count = nullptr; P.fix_phase = nullptr; P.fix_cap = FQ_FIX_CAP;
+    fq_kernel_t kf = pick_fq_kernel(P.W.k, P.W.m, P.W.has_query != 0 || P.W.sp_dense || P.W.sp_keys);
+    uint64_t want = (n_chunks_max + fqw::WARPS - 1) / fqw::WARPS;
+    const unsigned grid = (unsigned)(want < (uint64_t)st->fq_max_ctas ? want : (uint64_t)st->fq_max_ctas);
+    kf<<<grid, fqw::NT, sizeof(fqw::Smem), ctx->stream>>>(P);
+    fqw::k_verify<<<1, fqw::VT, 0, ctx->stream>>>(info, P.start, cb, st->fq_fix_list, st->fq_fix_phase, st->fq_counters + 4 * wi + 2, FQ_FIX_CAP, &c->flags,
+                                                  P.carry, n_vis, st->fq_words + wo, &c->fin[3]);
+    P.fix_list = st->fq_fix_list; P.fix_count = st->fq_counters + 4 * wi + 2; P.fix_phase = st->fq_fix_phase; P.ticket = st->fq_counters + 4 * wi + 1;
+    kf<<<(unsigned)ctx->sm_count, fqw::NT, sizeof(fqw::Smem), ctx->stream>>>(P);      // fix-up: chunks without a local guess (usually none)
+    ctx->launches += 3;
+    NTG_CUDA(ctx, cudaGetLastError());
+    if (final) {
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_k1, ctx->stream));
+        if (reduce) { fused::k_reduce_copy<<<1, 32, 0, ctx->stream>>>(c->tallies, &c->flags, &c->fin[3], n_vis, st->reduce_buf); ctx->launches++; }
+    }
+    if (!reduce) {
+        NTG_CUDA(ctx, cudaMemcpyAsync(st->h_ctl + ci, c, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_done[ci], ctx->stream));
+    }
+    return NTG_OK;
+}
+
+// how a pass runs: fused::k_fused without / with speculated FASTQ line phases, or the record-owned fast path (short-read FASTQ)
+enum PassMode { MODE_NOSPEC = 0, MODE_SPEC = 1, MODE_FQ = 2 };
+static PassShape pass_shape(const uint8_t* sample, size_t ns, int format, const ntg_tally_config* cfg) {
+    PassShape sh;
+    sh.tile_bytes = pick_tile_bytes(sample, ns, format);
+    sh.fq_ok = format == NTG_FMT_FASTQ && !(cfg->flags & (NTG_TALLY_NO_FASTPATH | NTG_TALLY_NO_SPECULATION)) && fq_shape(sample, ns, &sh.cb, &sh.frags);
+    return sh;
+}
+
 // ---- a pass over bytes resident in device memory: one launch -----------------------------------------------------
-static int pass_resident(ntg_ctx* ctx, const uint8_t* dbytes, uint64_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec,
+static int pass_resident(ntg_ctx* ctx, const uint8_t* dbytes, uint64_t n, int format, const ntg_tally_config* cfg, const PassShape& sh, int mode,
                          PassResult* out) {
     FusedState* st = ctx->fused;
+    const uint32_t tile_bytes = sh.tile_bytes;
+    const bool spec = mode != MODE_NOSPEC;
+    if (mode == MODE_FQ) {
+        NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, true, 0, 0));
+        NTG_TRY(fq_enqueue_launch(ctx, dbytes, n, n, sh.cb, sh.frags, 0, true, 0));
+        NTG_CUDA(ctx, cudaEventSynchronize(st->ev_done[0]));
+        *out = PassResult{};
+        out->add(st->h_ctl[0]);
+        out->fq_next = st->h_ctl[0].fin[3];
+        return NTG_OK;
+    }
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
     NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, spec, num_tiles, num_tiles));
     NTG_TRY(fused_enqueue_launch(ctx, dbytes, 0, n, 0, num_tiles, true, 0));
@@ -266,6 +410,8 @@ struct SegmentFeed {
     uint64_t checked = 0;            // launches whose control block has been read back
     struct Rec { uint64_t tb, te, n_vis; size_t len; bool final; } recs[NCTL] = {};
     size_t seg_target = STREAM_SEG;  // bytes of whole tiles per launch (device-side inflate uses larger segments)
+    bool fq = false; uint32_t cb = 0, frags = 1;    // record-owned fast path: launches are byte ranges, chained by their carry words
+    uint64_t bytes_submitted = 0;
 
     int open(ntg_ctx* c, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec, size_t seg_bytes = STREAM_SEG) {
         ctx = c;
@@ -303,14 +449,21 @@ struct SegmentFeed {
         else if (len) NTG_CUDA(ctx, cudaMemcpyAsync(buf + STREAM_BACK, src, len, cudaMemcpyHostToDevice, ctx->copy_stream));
         NTG_CUDA(ctx, cudaEventRecord(st->ev_copy[b], ctx->copy_stream));
         NTG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, st->ev_copy[b], 0));
+        if (L == 0) NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
+        if (fq) {
+            const uint64_t start = bytes_submitted, n_vis = final ? n_total : start + len;
+            NTG_TRY(fq_enqueue_launch(ctx, buf + STREAM_BACK - start, n_vis, len + 2 * (uint64_t)fqw::WIN, cb, frags, L, final, ci));
+            recs[ci] = Rec{0, 0, n_vis, len, final};
+            prev_len = len; bytes_submitted += len; L++;
+            return NTG_OK;
+        }
         const uint64_t tb = next_tile, start = tb * (uint64_t)TB;
         const uint64_t te = final ? (n_total + TB - 1) / TB : tb + len / TB;
         const uint64_t n_vis = final ? n_total : te * (uint64_t)TB;
         const uint64_t gmin = start > STREAM_BACK ? start - STREAM_BACK : 0;
-        if (L == 0) NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
         NTG_TRY(fused_enqueue_launch(ctx, buf + STREAM_BACK - start, gmin, n_vis, tb, te, final, ci));
         recs[ci] = Rec{tb, te, n_vis, len, final};
-        prev_len = len; next_tile = te; L++;
+        prev_len = len; next_tile = te; bytes_submitted += len; L++;
         st->epoch_tiles = te;                                     // generations this pass has used so far
         return NTG_OK;
     }
@@ -333,13 +486,14 @@ struct SegmentFeed {
     }
 };
 
-static int pass_host(ntg_ctx* ctx, const uint8_t* bytes, uint64_t n, int format, const ntg_tally_config* cfg, uint32_t tile_bytes, bool spec,
+static int pass_host(ntg_ctx* ctx, const uint8_t* bytes, uint64_t n, int format, const ntg_tally_config* cfg, const PassShape& sh, int mode,
                      PassResult* out) {
     SegmentFeed f;
-    NTG_TRY(f.open(ctx, format, cfg, tile_bytes, spec));
+    f.fq = mode == MODE_FQ; f.cb = sh.cb; f.frags = sh.frags;
+    NTG_TRY(f.open(ctx, format, cfg, sh.tile_bytes, mode != MODE_NOSPEC));
     *out = PassResult{};
-    auto check = [&](uint64_t, const LaunchCtl& c) { out->add(c); return (int)NTG_OK; };
-    const uint64_t seg_bytes = f.seg_tiles() * (uint64_t)tile_bytes;
+    auto check = [&](uint64_t, const LaunchCtl& c) { out->add(c); if (f.fq) out->fq_next = c.fin[3]; return (int)NTG_OK; };
+    const uint64_t seg_bytes = f.fq ? (uint64_t)STREAM_SEG : f.seg_tiles() * (uint64_t)sh.tile_bytes;
     uint64_t off = 0;
     for (;;) {
         const bool final = n - off <= seg_bytes;
@@ -385,16 +539,43 @@ static int classify_error_at(ntg_ctx* ctx, const ByteSource& src, uint64_t E, ui
     }
 }
 
-// Whole-input tallies with the reference's iterator semantics.  `run(n_eff, spec, &result)` makes one pass over the first
+// The tail of a record-owned pass: the bytes from the first record that was not complete to the end of the stream (at most one
+// record and blank lines) go through the exact record-table path; its tallies join, its error (if any) is the stream's.
+static int fq_tail(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, PassResult* r, ntg_parse_error* err) {
+    if (r->fq_next >= src.n) return NTG_OK;
+    ByteSource tail{src.host ? src.host + r->fq_next : nullptr, src.dev ? src.dev + r->fq_next : nullptr, src.n - r->fq_next, src.more_behind};
+    PassResult x; ntg_parse_error e2;
+    NTG_TRY(exact_tally(ctx, tail, format, cfg, &x, &e2));
+    const uint64_t before = r->tallies[0];
+    for (int i = 0; i < 9; i++) r->tallies[i] += x.tallies[i];
+    if (e2.kind && err) { *err = e2; err->record_index += before; err->line += 4 * before; }
+    return NTG_OK;
+}
+
+// Whole-input tallies with the reference's iterator semantics.  `run(n_eff, mode, &result)` makes one pass over the first
 // n_eff bytes of the source (resident or streamed); every pass can be repeated because the caller still holds the bytes.
 template <typename Run>
-static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, Run&& run, ntg_tallies* out, ntg_parse_error* err) {
+static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, bool fq_ok, Run&& run, ntg_tallies* out,
+                       ntg_parse_error* err) {
     if (err) { std::memset(err, 0, sizeof(*err)); err->format = format; }
     PassResult r;
-    NTG_TRY(run(src.n, true, &r));
     uint32_t spec_missed = 0;
-    if (r.flags & fused::FLAG_SPEC_MISS) { spec_missed = r.flags; NTG_TRY(run(src.n, false, &r)); }   // a speculated FASTQ line phase was wrong
-    if (r.flags == 0) { tallies_from_pass(r, out); out->reserved[1] = spec_missed; return NTG_OK; }
+    bool fq = false;
+    if (fq_ok) {
+        // the record-owned fast path takes clean streams and streams whose only problem is a failing record; anything else
+        // (a wrong phase guess, a record longer than its slack, a newline-dense chunk) is fused::k_fused's business
+        NTG_TRY(run(src.n, MODE_FQ, &r));
+        fq = r.flags == 0 || (r.flags == fused::FLAG_PARSE_ERROR && r.err_key != ~0ull);
+    }
+    if (!fq) {
+        NTG_TRY(run(src.n, MODE_SPEC, &r));
+        if (r.flags & fused::FLAG_SPEC_MISS) { spec_missed = r.flags; NTG_TRY(run(src.n, MODE_NOSPEC, &r)); }   // a speculated FASTQ line phase was wrong
+    }
+    if (r.flags == 0) {
+        if (fq) NTG_TRY(fq_tail(ctx, src, format, cfg, &r, err));
+        tallies_from_pass(r, out); out->reserved[1] = spec_missed;
+        return NTG_OK;
+    }
     const uint32_t why = r.flags;
     if (r.flags == fused::FLAG_PARSE_ERROR && format == NTG_FMT_FASTA) {
         // only the end-of-stream rule can fail (fasta.rs:348-356): the last record is not delivered, nothing of it was tallied
@@ -408,8 +589,12 @@ static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const nt
         const uint64_t E = r.err_key >> 2;
         PassResult t;
         if (E >= 2) {
-            NTG_TRY(run(E, true, &t));
-            if (t.flags & fused::FLAG_SPEC_MISS) NTG_TRY(run(E, false, &t));
+            bool done = false;
+            if (fq) { NTG_TRY(run(E, MODE_FQ, &t)); done = t.flags == 0 && t.fq_next >= E; }
+            if (!done) {
+                NTG_TRY(run(E, MODE_SPEC, &t));
+                if (t.flags & fused::FLAG_SPEC_MISS) NTG_TRY(run(E, MODE_NOSPEC, &t));
+            }
         }
         if (t.flags == 0) {
             bool confirmed = false;

@@ -275,9 +275,9 @@ int ntg_bitkmer_minimizer(ntg_ctx* ctx, const uint64_t* in, size_t n, uint32_t k
 // ---- (3) fused hot path ------------------------------------------------------------------------
 // sniff + tile sizing of a resident buffer from its first 64 KiB (one small D2H), cached per (pointer, size): repeated calls
 // on the same buffer skip the host round trip, and k_finalize verifies the format byte on the device (FLAG_FORMAT).
-static int resident_sniff(ntg_ctx* ctx, uint64_t dptr, size_t n, bool use_cache, int* format, uint32_t* tile_bytes) {
+static int resident_sniff(ntg_ctx* ctx, uint64_t dptr, size_t n, bool use_cache, const ntg_tally_config* cfg, int* format, PassShape* shape) {
     FusedState* st = ctx->fused;
-    if (use_cache && st->sniff_ptr == dptr && st->sniff_n == n && st->sniff_format) { *format = st->sniff_format; *tile_bytes = st->sniff_tile; return NTG_OK; }
+    if (use_cache && st->sniff_ptr == dptr && st->sniff_n == n && st->sniff_format && st->sniff_flags == cfg->flags) { *format = st->sniff_format; *shape = st->sniff_shape; return NTG_OK; }
     static thread_local std::vector<uint8_t> sample;
     const size_t ns = n < 65536 ? n : 65536;
     sample.resize(ns);
@@ -286,17 +286,17 @@ static int resident_sniff(ntg_ctx* ctx, uint64_t dptr, size_t n, bool use_cache,
     const uint8_t b0 = sample[0];
     *format = b0 == '>' ? NTG_FMT_FASTA : (b0 == '@' ? NTG_FMT_FASTQ : NTG_FMT_NONE);
     if (*format == NTG_FMT_NONE) return ntg_set_error(ctx, NTG_EUNKNOWN_FORMAT, "first byte is neither '>' nor '@'");
-    *tile_bytes = pick_tile_bytes(sample.data(), ns, *format);
-    st->sniff_ptr = dptr; st->sniff_n = n; st->sniff_format = *format; st->sniff_tile = *tile_bytes;
+    *shape = pass_shape(sample.data(), ns, *format, cfg);
+    st->sniff_ptr = dptr; st->sniff_n = n; st->sniff_format = *format; st->sniff_shape = *shape; st->sniff_flags = cfg->flags;
     return NTG_OK;
 }
 static int tally_resident(ntg_ctx* ctx, uint64_t dptr, size_t n, const ntg_tally_config* cfg, ntg_tallies* out, ntg_parse_error* err) {
-    int format; uint32_t tile_bytes;
+    int format; PassShape sh;
     NTG_TRY(fused_init(ctx));
-    NTG_TRY(resident_sniff(ctx, dptr, n, false, &format, &tile_bytes));
+    NTG_TRY(resident_sniff(ctx, dptr, n, false, cfg, &format, &sh));
     const ByteSource src{nullptr, (const uint8_t*)(uintptr_t)dptr, n};
-    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_resident(ctx, src.dev, n_eff, format, cfg, tile_bytes, spec, r); };
-    return tally_whole(ctx, src, format, cfg, run, out, err);
+    auto run = [&](uint64_t n_eff, int mode, PassResult* r) { return pass_resident(ctx, src.dev, n_eff, format, cfg, sh, mode, r); };
+    return tally_whole(ctx, src, format, cfg, sh.fq_ok, run, out, err);
 }
 
 int ntg_tally_fastx_device_enqueue(ntg_ctx* ctx, uint64_t dptr, size_t n, const ntg_tally_config* cfg) {
@@ -307,14 +307,23 @@ int ntg_tally_fastx_device_enqueue(ntg_ctx* ctx, uint64_t dptr, size_t n, const 
     if (st->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is already pending: collect it first");
     if (n < 2 || !dptr) return ntg_set_error(ctx, NTG_EINVAL, "enqueue needs >= 2 device-resident bytes (use ntg_tally_fastx_device for the sniff rules)");
     if ((dptr & 15) != 0) return ntg_set_error(ctx, NTG_EINVAL, "device pointer must be 16-byte aligned");
-    int format; uint32_t tile_bytes;
-    NTG_TRY(resident_sniff(ctx, dptr, n, true, &format, &tile_bytes));
+    int format; PassShape sh;
+    NTG_TRY(resident_sniff(ctx, dptr, n, true, cfg, &format, &sh));
+    const uint32_t tile_bytes = sh.tile_bytes;
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
-    NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, true, num_tiles, num_tiles));
     const bool reduce = (cfg->flags & NTG_TALLY_ALLREDUCE) != 0;
     if (reduce && !ctx->nccl_comm) return ntg_set_error(ctx, NTG_EINVAL, "NTG_TALLY_ALLREDUCE needs ntg_comm_init");
-    NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
-    NTG_TRY(fused_enqueue_launch(ctx, (const uint8_t*)(uintptr_t)dptr, 0, n, 0, num_tiles, true, 0, reduce));
+    st->pending_fq = sh.fq_ok;
+    if (sh.fq_ok) {
+        // the record-owned fast path; collect falls back to the full logic when it reports anything but a clean, tail-less pass
+        NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, true, 0, 0));
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
+        NTG_TRY(fq_enqueue_launch(ctx, (const uint8_t*)(uintptr_t)dptr, n, n, sh.cb, sh.frags, 0, true, 0, reduce));
+    } else {
+        NTG_TRY(fused_begin_pass(ctx, format, cfg, tile_bytes, true, num_tiles, num_tiles));
+        NTG_CUDA(ctx, cudaEventRecord(st->ev_k0, ctx->stream));
+        NTG_TRY(fused_enqueue_launch(ctx, (const uint8_t*)(uintptr_t)dptr, 0, n, 0, num_tiles, true, 0, reduce));
+    }
     if (reduce) {
         // tallies -> NCCL send buffer was done by k_finalize: all-reduce in-stream, then both results come back with one wait
         int r = nccldyn::AllReduce(st->reduce_buf, st->reduce_buf, 16, nccldyn::kUint64, nccldyn::kSum, ctx->nccl_comm, ctx->stream);
@@ -337,6 +346,7 @@ int ntg_tally_fastx_device_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_err
     if (fused_kernel_ms) NTG_CUDA(ctx, cudaEventElapsedTime(fused_kernel_ms, st->ev_k0, st->ev_k1));
     if (err) { std::memset(err, 0, sizeof(*err)); err->format = st->format; }
     const LaunchCtl& c = st->h_ctl[0];
+    const bool clean = c.flags == 0 && (!st->pending_fq || c.fin[3] >= st->pend_n);      // (a record-owned pass with a tail needs the host)
     if (st->pending_reduce) {
         // every rank clean: the reduced tallies are the answer.  Otherwise each rank resolves its own shard (replay / exact
         // path) and the caller reduces with ntg_comm_allreduce_tallies — reserved[0] tells which case this is.
@@ -345,8 +355,8 @@ int ntg_tally_fastx_device_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_err
             tallies_from_pass(r, out);
             return NTG_OK;
         }
-        if (c.flags == 0) { PassResult r; r.add(c); tallies_from_pass(r, out); out->reserved[0] = NTG_RESERVED_NOT_REDUCED; return NTG_OK; }
-    } else if (c.flags == 0) { PassResult r; r.add(c); tallies_from_pass(r, out); return NTG_OK; }
+        if (clean) { PassResult r; r.add(c); tallies_from_pass(r, out); out->reserved[0] = NTG_RESERVED_NOT_REDUCED; return NTG_OK; }
+    } else if (clean) { PassResult r; r.add(c); tallies_from_pass(r, out); return NTG_OK; }
     if (c.flags & fused::FLAG_FORMAT) st->sniff_format = 0;          // the buffer changed format since it was sniffed
     ntg_tally_config cfg = st->cfg; cfg.flags &= ~NTG_TALLY_ALLREDUCE;
     const int rc = tally_resident(ctx, st->pend_dptr, st->pend_n, &cfg, out, err);
@@ -380,10 +390,10 @@ int ntg_tally_fastx(ntg_ctx* ctx, const uint8_t* bytes, size_t n, const ntg_tall
     int format;
     if (sniff_format(ctx, n ? bytes[0] : 0, n, out, err, &format)) return NTG_OK;
     NTG_TRY(fused_init(ctx));
-    const uint32_t tile_bytes = pick_tile_bytes(bytes, n < 65536 ? n : 65536, format);
+    const PassShape sh = pass_shape(bytes, n < 65536 ? n : 65536, format, cfg);
     const ByteSource src{bytes, nullptr, n};
-    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_host(ctx, bytes, n_eff, format, cfg, tile_bytes, spec, r); };
-    return tally_whole(ctx, src, format, cfg, run, out, err);
+    auto run = [&](uint64_t n_eff, int mode, PassResult* r) { return pass_host(ctx, bytes, n_eff, format, cfg, sh, mode, r); };
+    return tally_whole(ctx, src, format, cfg, sh.fq_ok, run, out, err);
 }
 
 // ---- (3b) streaming session: parse_fastx_reader<R: Read> for the tally path --------------------
@@ -542,10 +552,10 @@ int ntg_spectrum_add_fastx_device(ntg_spectrum* sp, uint64_t dptr, size_t n, ntg
     SPECTRUM_ENTER(sp);
     ntg_ctx* ctx = sp->ctx;
     if (n < 2 || !dptr || (dptr & 15)) return ntg_set_error(ctx, NTG_EINVAL, "spectrum: >= 2 device-resident bytes at a 16-byte aligned address");
-    int format; uint32_t tile_bytes;
-    NTG_TRY(resident_sniff(ctx, dptr, n, false, &format, &tile_bytes));
+    int format; PassShape sh;
     const ntg_tally_config cfg = spectrum_cfg(sp);
-    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_resident(ctx, (const uint8_t*)(uintptr_t)dptr, n_eff, format, &cfg, tile_bytes, spec, r); };
+    NTG_TRY(resident_sniff(ctx, dptr, n, false, &cfg, &format, &sh));
+    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_resident(ctx, (const uint8_t*)(uintptr_t)dptr, n_eff, format, &cfg, sh, spec ? MODE_SPEC : MODE_NOSPEC, r); };
     return spectrum_add_input(sp, n, format, run, tallies, err);
 }
 int ntg_spectrum_add_fastx(ntg_spectrum* sp, const uint8_t* bytes, size_t n, ntg_tallies* tallies, ntg_parse_error* err) {
@@ -555,9 +565,9 @@ int ntg_spectrum_add_fastx(ntg_spectrum* sp, const uint8_t* bytes, size_t n, ntg
     int format;
     ntg_tallies scratch;
     if (sniff_format(ctx, n ? bytes[0] : 0, n, tallies ? tallies : &scratch, err, &format)) return NTG_OK;
-    const uint32_t tile_bytes = pick_tile_bytes(bytes, n < 65536 ? n : 65536, format);
     const ntg_tally_config cfg = spectrum_cfg(sp);
-    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_host(ctx, bytes, n_eff, format, &cfg, tile_bytes, spec, r); };
+    const PassShape sh = pass_shape(bytes, n < 65536 ? n : 65536, format, &cfg);
+    auto run = [&](uint64_t n_eff, bool spec, PassResult* r) { return pass_host(ctx, bytes, n_eff, format, &cfg, sh, spec ? MODE_SPEC : MODE_NOSPEC, r); };
     return spectrum_add_input(sp, n, format, run, tallies, err);
 }
 int ntg_spectrum_count(ntg_spectrum* sp, const uint8_t* kmer, uint64_t* count) {
