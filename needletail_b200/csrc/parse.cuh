@@ -206,7 +206,7 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         // -------------------------------------------------------------------------- FASTQ
         uint32_t n_complete = n_nl / 4, rem = n_nl % 4;
         DevBuf<uint8_t> errkind; DevBuf<uint32_t> first_err;
-        if (drecs.alloc(n_complete) || errkind.alloc(n_complete) || first_err.alloc(1))
+        if (drecs.alloc((size_t)n_complete + 1) || errkind.alloc(n_complete) || first_err.alloc(1))      // (+1: a last record without newline)
             return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
         PCUDA(cudaMemsetAsync(first_err.p, 0xFF, 4, ctx->stream));
         if (n_complete) {
@@ -274,7 +274,10 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         uint64_t total = n_ok + (have_eof_rec ? 1 : 0);
         if (priv->recs.alloc(total)) return done(ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed"));
         if (n_ok) PCUDA(cudaMemcpy(priv->recs.p, drecs.p, n_ok * sizeof(ntg_record), cudaMemcpyDeviceToHost));
-        if (have_eof_rec) priv->recs.p[n_ok] = eof_rec;
+        if (have_eof_rec) {
+            priv->recs.p[n_ok] = eof_rec;
+            PCUDA(cudaMemcpy(drecs.p + n_ok, &eof_rec, sizeof(eof_rec), cudaMemcpyHostToDevice));      // (callers that keep the device table)
+        }
         res->n_records = total; res->records = priv->recs.p;
         // FastxReader::position() after the last next(): position of the last record attempted (fastq.rs:411-415)
         {
