@@ -219,6 +219,8 @@ typedef struct ntg_tally_config {
 /* diagnostic: short-read FASTQ goes through the general tile kernel (fused::k_fused) instead of the record-owned fast path */
 #define NTG_TALLY_NO_FASTPATH 4u
 #define NTG_RESERVED_NOT_REDUCED (1ull << 32)
+/* reserved[1] bit: the record-owned short-read FASTQ kernel (fastq_warp.cuh) produced the tallies (whole-buffer entry points) */
+#define NTG_RESERVED_FAST_PATH (1ull << 32)
 
 typedef struct ntg_tallies {
     uint64_t n_records;

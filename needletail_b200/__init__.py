@@ -424,7 +424,8 @@ class Context:
         d["err_kind"] = ERROR_KINDS.get(e.kind) if e.kind else None
         d["err_line"] = int(e.line)
         d["fallback"] = int(t.reserved[0]) & 0xFFFFFFFF      # 0: the single-pass fused kernel produced the tallies
-        d["ws_handover"] = int(t.reserved[1])   # != 0: the warp-specialised kernel handed over to the general fused kernel
+        d["ws_handover"] = int(t.reserved[1]) & 0xFFFFFFFF   # != 0: a speculated FASTQ line phase was wrong and the pass re-ran without speculation
+        d["fast_path"] = bool(int(t.reserved[1]) >> 32)       # the record-owned short-read FASTQ kernel produced the tallies
         d["ws_cycles"] = {"claim": int(t.reserved[2]), "scan": int(t.reserved[3]), "lookback_retry": int(t.reserved[4]),
                           "walker_wait": int(t.reserved[5]), "walker_work": int(t.reserved[6])}
         return d

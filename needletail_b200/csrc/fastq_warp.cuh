@@ -63,6 +63,64 @@ struct __align__(16) Smem {
     uint64_t red[WARPS][9];
 };
 
+// Newlines of one 256-byte row, as a loop (fused::scan_row is the same test fully unrolled: 8 KB of code per call site, and
+// with every warp of an SM in a different phase of its chunk the instruction cache was this kernel's largest stall).  The
+// lane reads 16-byte column (j + lane) & 15 at step j (bank-conflict free for rows 256 B apart) and sets the mask bits of
+// that column directly.
+__device__ __forceinline__ void scan_row_loop(const uint32_t* __restrict__ row, uint32_t lane, uint32_t& cnt, uint64_t& mask) {
+    const uint4* __restrict__ row4 = reinterpret_cast<const uint4*>(row);
+    uint32_t acc = 0; uint64_t m = 0;
+    auto test = [](uint32_t w) -> uint32_t {
+        const uint32_t x = w ^ 0x0A0A0A0Au;
+        return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;      // 0x80 in every byte that is exactly '\n'
+    };
+#pragma unroll 1
+    for (uint32_t j = 0; j < 16; j++) {
+        const uint32_t col = (j + lane) & 15u;
+        const uint4 v = row4[col];
+        const uint32_t z0 = test(v.x), z1 = test(v.y), z2 = test(v.z), z3 = test(v.w);
+        acc += (z0 >> 7) + (z1 >> 7) + (z2 >> 7) + (z3 >> 7);                // <= 64 per byte lane over the row
+        const uint32_t nib = (z0 ? 1u : 0u) | (z1 ? 2u : 0u) | (z2 ? 4u : 0u) | (z3 ? 8u : 0u);
+        m |= (uint64_t)nib << (4u * col);
+    }
+    const uint32_t t = (acc & 0x00FF00FFu) + ((acc >> 8) & 0x00FF00FFu);
+    cnt = (t & 0xFFFFu) + (t >> 16);
+    mask = m;
+}
+
+// One fragment [ap, bp) of the sequence line that starts at a (ap == a for the first fragment: no warm-up; later fragments
+// warm up over the k-1 bases in front of them, inside their own line).  fused::run_item without the warm-up-from-codes variant
+// (a line start has nothing in front of it), i.e. with one copy of the clean walker instead of two.
+template <int KW, bool MINI, int W, int FK, int FM>
+__device__ __forceinline__ void run_fragment(const uint8_t* sb, const uint8_t* lut, const uint32_t* rins, const uint32_t* comb, int a, int ap, int bp,
+                                             const fused::Params& P, fused::Acc& acc, uint32_t& slow, uint32_t& mode) {
+    int b = bp;
+    if (b > ap && sb[b - 1] == '\r') b--;                  // a trailing '\r' is deleted by normalize: nothing to walk
+    if (b <= ap) return;
+    const int ws = ap > a ? fused::find_ws(sb, lut, ap, a, true, (int)P.k, slow) : a;
+    constexpr bool ONE = FK >= 21 && FK <= 31;
+    if (FK > 32) {
+        if (!__any_sync(__activemask(), mode != 0u) && fused::walk_clean2<(FK > 32 ? FK : 51)>(sb, comb, ws, b, acc)) return;
+        mode = 1u;
+        uint32_t any_bad = 0;
+        for (int q = ws; q < b; q++) any_bad |= lut[sb[q]];
+        if (any_bad <= 3u) mode = 0u;
+        fused::walk<KW, MINI, W>(sb, lut, ws, ap, b, P, acc, false);
+    } else if (ONE) {
+        constexpr int CK = ONE ? FK : 21, CM = ONE ? FM : 0;
+        bool done = false;
+        if (!__any_sync(__activemask(), mode != 0u)) done = fused::walk_clean<CK, CM, false>(sb, comb, ws, b, 0, acc);
+        if (!done) {
+            uint32_t seen = 0x80u;
+            done = fused::walk_fast_cold<CK, CM>(sb, lut, rins, ws, b, acc, &seen);
+            mode = seen > 3u ? 1u : 0u;
+        }
+        if (!done) fused::walk_slow<KW, MINI, W>(sb, lut, ws, ap, b, P, acc, false);
+    } else {
+        fused::walk<KW, MINI, W>(sb, lut, ws, ap, b, P, acc, false);
+    }
+}
+
 template <int KW, bool MINI, int W, int FK, int FM>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_records(const Params P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -89,14 +147,25 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_records(const Params P) {
     fused::Acc acc;
     const bool FIX = P.fix_list != nullptr;                           // fix-up launch: chunks and their true phases come from k_verify
     const uint32_t n_fix = FIX ? min(*P.fix_count, P.fix_cap) : 0u;
+    // Chunks are independent, so a warp claims its NEXT chunk while it starts on the current one and asks for it to be pulled into
+    // L2 (cp.async.bulk.prefetch.L2): the bulk copy that later stages it then pays an L2 round trip instead of an HBM one.
+    uint32_t c_next = 0;
+    if (lane == 0) c_next = atomicAdd(P.ticket, 1u);
+    c_next = __shfl_sync(0xffffffffu, c_next, 0);
     for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(P.ticket, 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
+        uint32_t c = c_next;
         uint32_t given = 4;
         if (FIX) { if (c >= n_fix) break; given = P.fix_phase[c]; c = P.fix_list[c]; }
         const uint64_t lo = A + (uint64_t)c * CB;
         if (lo >= P.n_vis) break;
+        if (lane == 0) {
+            c_next = atomicAdd(P.ticket, 1u);
+            if (!FIX) {
+                const uint64_t nlo = A + (uint64_t)c_next * CB;
+                if (nlo < P.n_vis) { const uint32_t nb = (uint32_t)min((uint64_t)WINB, P.n_vis - nlo) & ~15u; if (nb) fused::bulk_prefetch_l2(P.bytes + nlo, nb); }
+            }
+        }
+        c_next = __shfl_sync(0xffffffffu, c_next, 0);
         const uint32_t avail = (uint32_t)min((uint64_t)WINB, P.n_vis - lo);
         const uint32_t halo = lo ? HALO : 0;
         const uint32_t bulk = avail & ~15u;
@@ -110,11 +179,11 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_records(const Params P) {
         __syncwarp();
         // ---- newlines of the window: rows lane and lane + 32, ordered list by two warp scans
         uint32_t cnt[2]; uint64_t wm[2];
-#pragma unroll
+#pragma unroll 1
         for (int rd = 0; rd < 2; rd++) {
             cnt[rd] = 0; wm[rd] = 0;
             const uint32_t row = rd * 32 + lane;
-            if (row < (uint32_t)ROWS && row * fused::ROWB < avail) fused::scan_row(reinterpret_cast<const uint32_t*>(B.win) + row * fused::ROWW, lane, cnt[rd], wm[rd]);
+            if (row < (uint32_t)ROWS && row * fused::ROWB < avail) scan_row_loop(reinterpret_cast<const uint32_t*>(B.win) + row * fused::ROWW, lane, cnt[rd], wm[rd]);
         }
         uint32_t inc = cnt[0] | (cnt[1] << 16);                      // (a row holds at most 256 newlines, a round at most 8192)
 #pragma unroll
@@ -210,7 +279,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_records(const Params P) {
             }
             const int len = b - a;
             const int ap = a + (int)(((int64_t)len * part) / frags), bp = a + (int)(((int64_t)len * (part + 1)) / frags);
-            fused::run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, ap, bp, a, true, P.W, acc, false, slow, mode);
+            run_fragment<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, ap, bp, P.W, acc, slow, mode);
         }
         __syncwarp();
     }
@@ -243,10 +312,15 @@ __global__ void __launch_bounds__(VT) k_verify(const uint8_t* __restrict__ info,
     const uint32_t tid = threadIdx.x;
     const uint64_t A = *start & ~15ull;
     const uint32_t n_chunks = n_vis > A ? (uint32_t)((n_vis - A + cb - 1) / cb) : 0u;
-    const uint32_t per = (n_chunks + VT - 1) / VT;
-    const uint32_t b = min(tid * per, n_chunks), e = min(b + per, n_chunks);
+    // 16 chunks per load (the info array is zero-padded to whole vectors by the host)
+    const uint4* __restrict__ info4 = reinterpret_cast<const uint4*>(info);
+    const uint32_t nvec = (n_chunks + 15u) / 16u;
+    const uint32_t per = (nvec + VT - 1) / VT;
+    const uint32_t b = min(tid * per, nvec), e = min(b + per, nvec);
+    auto s3 = [](uint32_t w) -> uint32_t { return ((w & 0x03030303u) * 0x01010101u) >> 24; };      // sum of the four 2-bit counts
     uint32_t sum = 0;
-    for (uint32_t i = b; i < e; i++) sum += info[i] & 3u;
+#pragma unroll 4
+    for (uint32_t i = b; i < e; i++) { const uint4 x = info4[i]; sum += s3(x.x) + s3(x.y) + s3(x.z) + s3(x.w); }
     s_sum[tid] = sum;
     __syncthreads();
     for (uint32_t d = 1; d < VT; d <<= 1) {                          // inclusive scan (Hillis-Steele; once per launch)
@@ -256,15 +330,23 @@ __global__ void __launch_bounds__(VT) k_verify(const uint8_t* __restrict__ info,
         __syncthreads();
     }
     uint32_t pre = s_sum[tid] - sum, bad = 0;
+#pragma unroll 2
     for (uint32_t i = b; i < e; i++) {
-        const uint8_t v = info[i];
-        const uint32_t g = (v >> 2) & 7u, truth = pre & 3u;
-        if (v & INFO_UNRESOLVED) {
-            const uint32_t o = atomicAdd(fix_count, 1u);
-            if (o < fix_cap) { fix_list[o] = i; fix_phase[o] = (uint8_t)truth; } else bad |= fused::FLAG_SPEC_MISS;
-        } else if ((v & INFO_DONE) && g < 4 && g != truth) bad |= fused::FLAG_SPEC_MISS;
-        else if (!(v & (INFO_DONE | INFO_UNRESOLVED))) bad |= fused::FLAG_SPEC_MISS;      // (a chunk nobody claimed: cannot happen)
-        pre += v & 3u;
+        const uint4 x = info4[i];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const uint32_t ci = i * 16u + q;
+            const uint32_t v = (w[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+            if (ci < n_chunks) {
+                const uint32_t g = (v >> 2) & 7u, truth = pre & 3u;
+                if (v & INFO_UNRESOLVED) {
+                    const uint32_t o = atomicAdd(fix_count, 1u);
+                    if (o < fix_cap) { fix_list[o] = ci; fix_phase[o] = (uint8_t)truth; } else bad |= fused::FLAG_SPEC_MISS;
+                } else if (!(v & INFO_DONE) || (g < 4 && g != truth)) bad |= fused::FLAG_SPEC_MISS;      // wrong guess (or a chunk nobody claimed)
+            }
+            pre += v & 3u;
+        }
     }
     if (bad) atomicOr(flags, bad);
     if (tid == 0) {

@@ -131,6 +131,9 @@ static fq_kernel_t pick_fq_kernel(uint32_t k, uint32_t m, bool generic) {
     if (k - m + 1 == 11) return k_records<1, true, 11, 0, 0>;
     return k_records<1, true, 0, 0, 0>;
 }
+#ifndef NTG_FQ_MAX_FRAGS
+#define NTG_FQ_MAX_FRAGS 1
+#endif
 constexpr uint32_t FQ_FIX_CAP = 1u << 16;
 constexpr size_t FQ_INFO_SLOT = size_t(1) << 24;            // chunk bytes per launch slot (16 Mi chunks = 160 GB of text)
 static int fq_init(ntg_ctx* ctx) {
@@ -163,9 +166,11 @@ static bool fq_shape(const uint8_t* sample, size_t ns, uint32_t* cb, uint32_t* f
     for (size_t i = 0; i < ns; i++) nl += sample[i] == '\n';
     if (nl < 8) return false;
     const double rec = 4.0 * (double)ns / (double)nl;
+    // (fragments > 1 are implemented — reads up to ~600 bp — but measured slower than fused::k_fused on the 250 bp shape:
+    //  365 vs 440 Gbases/s, every fragment pays its own k-1 warm-up bases.  Until chunks can be larger, one fragment only.)
     uint32_t f = 1;
     while (f <= 4 && rec * 31.0 / f > fqw::CBMAX) f *= 2;
-    if (f > 4 || rec * 2.5 > fqw::SLACK) return false;
+    if (f > NTG_FQ_MAX_FRAGS || rec * 2.5 > fqw::SLACK) return false;
     uint32_t c = ((uint32_t)(rec * 31.0 / f) + 15u) & ~15u;
     if (c < 1024u) c = 1024u;
     if (c > (uint32_t)fqw::CBMAX) c = fqw::CBMAX;
@@ -331,9 +336,9 @@ static int fq_enqueue_launch(ntg_ctx* ctx, const uint8_t* base, uint64_t n_vis, 
     NTG_CUDA(ctx, cudaMemsetAsync(c, 0, sizeof(LaunchCtl), ctx->stream));
     NTG_CUDA(ctx, cudaMemsetAsync(&c->err_key, 0xFF, sizeof(c->err_key), ctx->stream));
     const uint64_t n_chunks_max = span / cb + 3;
-    if (n_chunks_max > st->fq_info_cap) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "launch too large for the record-owned path");
+    if (n_chunks_max + 64 > st->fq_info_cap) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "launch too large for the record-owned path");
     uint8_t* info = st->fq_info + (size_t)(seq & 1) * st->fq_info_cap;
-    NTG_CUDA(ctx, cudaMemsetAsync(info, 0, n_chunks_max, ctx->stream));
+    NTG_CUDA(ctx, cudaMemsetAsync(info, 0, (n_chunks_max + 63) & ~uint64_t(15), ctx->stream));      // (k_verify reads whole 16-byte vectors)
     NTG_CUDA(ctx, cudaMemsetAsync(st->fq_counters + 4 * wi, 0, 4 * sizeof(uint32_t), ctx->stream));
     NTG_CUDA(ctx, cudaMemsetAsync(st->fq_words + NCTL + wi, 0xFF, sizeof(unsigned long long), ctx->stream));
     if (first) NTG_CUDA(ctx, cudaMemsetAsync(st->fq_words + wi, 0, sizeof(unsigned long long), ctx->stream));
@@ -573,7 +578,7 @@ static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const nt
     }
     if (r.flags == 0) {
         if (fq) NTG_TRY(fq_tail(ctx, src, format, cfg, &r, err));
-        tallies_from_pass(r, out); out->reserved[1] = spec_missed;
+        tallies_from_pass(r, out); out->reserved[1] = spec_missed | (fq ? NTG_RESERVED_FAST_PATH : 0);
         return NTG_OK;
     }
     const uint32_t why = r.flags;
@@ -603,7 +608,7 @@ static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const nt
             if (confirmed) {
                 tallies_from_pass(t, out);
                 if (err) *err = e2;
-                out->reserved[1] = spec_missed;
+                out->reserved[1] = spec_missed | (fq ? NTG_RESERVED_FAST_PATH : 0);
                 return NTG_OK;
             }
         }

@@ -383,6 +383,42 @@ def test_synth_matches_oracle_and_tallies(ctx):
         ctx.device_free(d)
 
 
+def test_record_owned_fast_path_and_its_fallbacks(ctx):
+    """Short-read FASTQ goes through the record-owned kernel (fastq_warp.cuh); what it cannot take falls back to the tile
+    kernel with identical results; NTG_TALLY_NO_FASTPATH forces the tile kernel."""
+    rng = random.Random(77)
+    fq = O.gen_fastq(0x5EED0002, 0, 20000, 150, 655).tobytes()               # 6.3 MB: ~640 chunks
+    exp = O.tally_fastx(fq, k=31, m=21)
+    got = ctx.tally(fq, k=31, m=21)
+    assert got["fast_path"] and got["fallback"] == 0
+    for key in TALLY_KEYS:
+        assert got[key] == exp[key], key
+    ctx.tally_flags = 4
+    try:
+        slow = ctx.tally(fq, k=31, m=21)
+    finally:
+        ctx.tally_flags = 0
+    assert not slow["fast_path"]
+    for key in TALLY_KEYS:
+        assert slow[key] == exp[key], key
+    # every tail shape, CRLF, other k / m (generic walkers), reads of mixed length
+    for data in (fq[:-1], fq + b"\n\n", fq[:-200], fq[:len(fq) // 2 + 77], mutate_fastq(rng, 4000, 150, crlf=True), mutate_fastq(rng, 5000, 120)):
+        for k, m in ((31, 21), (21, 11), (15, 9), (51, 0), (31, 0)):
+            assert_tallies(ctx, data, k, m, what="fast path shapes")
+    # quality lines that start with '@' and '+' everywhere: no unique local evidence in many chunks -> fix-up launch / fallback
+    tricky = b"".join(b"@r%d\n" % i + bytes(rng.choice(b"ACGT") for _ in range(100)) + b"\n+\n" + rng.choice((b"@", b"+", b"I")) * 100 + b"\n" for i in range(6000))
+    t = assert_tallies(ctx, tricky, 31, 21, what="tricky quality lines")
+    assert t["n_records"] == 6000
+    # a long read in the middle (longer than the slack) and a phase-shifting error: tile kernel, same answers
+    long_rec = b"@long\n" + b"ACGT" * 2000 + b"\n+\n" + b"I" * 8000 + b"\n"
+    mixed = fq[: 316 * 500] + long_rec + fq[316 * 500:]
+    t = assert_tallies(ctx, mixed, 31, 21, what="long read inside short reads")
+    assert not t["fast_path"]
+    shifted = fq[: 316 * 700] + fq[316 * 700:].replace(b"\n+\n", b"\n", 1)
+    assert_tallies(ctx, shifted, 31, 21, what="a missing separator line")
+    assert_parse(ctx, shifted, "a missing separator line")
+
+
 def test_fast_path_is_taken_on_clean_files(ctx):
     fx = load_fixtures()
     assert ctx.tally(fx["data/28S.fasta"], k=31, m=21)["fallback"] == 0
