@@ -344,10 +344,10 @@ def run_ours(args):
     achieved = nbytes / (kavg * 1e-3) / 1e9
     ratio = load_traffic_ratio()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ratio * nbytes) if ratio else None, "kernel": "fused::k_fused<1,true,11,31,21>", "kernel_ms": kavg,
+                "traffic": (ratio * nbytes) if ratio else None, "kernel": "fqw::k_records<1,true,11,31,21> (+ k_verify, fix-up launch)", "kernel_ms": kavg,
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "traffic_note": "DRAM bytes per launch = ncu dram read+write bytes per input byte (profiles/traffic.json) x algorithmic bytes",
-                "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~42 SASS thread-instructions per base (31 in the walker loop, 19 of them on the 16-lane INT pipe, which is saturated while both CTAs of an SM walk; the scan / list / TMA phases of a tile leave it idle: 60 % busy overall); see DESIGN.md and profiles/r2*"}
+                "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~41 SASS thread-instructions per base, ~25 of them on the 16-lane INT pipe, which is 84 % busy in the record-owned kernel (ncu profiles/r2h_*; 63 % in the tile kernel it replaces for short-read FASTQ); see DESIGN.md"}
 
     # ---- end to end through the host-facing C-ABI call: pinned host FASTQ -> H2D -> fused kernel -> tallies
     e2e = None
