@@ -336,7 +336,7 @@ pub mod bitkmer {
 pub fn tally_fastx_file<P: AsRef<Path>>(path: P, k: u8, m: u8, inflate_threads: i32) -> Result<(sys::ntg_tallies, Option<ParseError>), ParseError> {
     let ctx = default_context()?;
     let ctx = ctx.lock().unwrap();
-    let cfg = sys::ntg_tally_config { k: k as u32, m: m as u32, allow_iupac: 0, has_query: 0, query: [0; 64], flags: 0 };
+    let cfg = sys::ntg_tally_config { k: k as u32, m: m as u32, allow_iupac: 0, has_query: 0, query: [0; 64], flags: 0, qmask_score: 0 };
     let (mut t, mut e) = (sys::ntg_tallies::default(), unsafe { std::mem::zeroed::<sys::ntg_parse_error>() });
     let c = CString::new(path.as_ref().to_string_lossy().as_bytes()).map_err(|_| empty_file())?;
     ctx.check(unsafe { sys::ntg_tally_fastx_file(ctx.raw, c.as_ptr(), &cfg, inflate_threads, &mut t, &mut e) })?;
@@ -346,7 +346,7 @@ pub fn tally_fastx_file<P: AsRef<Path>>(path: P, k: u8, m: u8, inflate_threads: 
 pub fn tally_fastx_reader<R: Read>(mut reader: R, k: u8, m: u8) -> Result<(sys::ntg_tallies, Option<ParseError>), ParseError> {
     let ctx = default_context()?;
     let ctx = ctx.lock().unwrap();
-    let cfg = sys::ntg_tally_config { k: k as u32, m: m as u32, allow_iupac: 0, has_query: 0, query: [0; 64], flags: 0 };
+    let cfg = sys::ntg_tally_config { k: k as u32, m: m as u32, allow_iupac: 0, has_query: 0, query: [0; 64], flags: 0, qmask_score: 0 };
     let mut s = ptr::null_mut();
     ctx.check(unsafe { sys::ntg_stream_open(ctx.raw, &cfg, &mut s) })?;
     let res = (|| {

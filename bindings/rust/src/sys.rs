@@ -45,7 +45,7 @@ pub struct ntg_items {
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct ntg_tally_config {
-    pub k: u32, pub m: u32, pub allow_iupac: u32, pub has_query: u32, pub query: [u8; 64], pub flags: u32,
+    pub k: u32, pub m: u32, pub allow_iupac: u32, pub has_query: u32, pub query: [u8; 64], pub flags: u32, pub qmask_score: u32,
 }
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]

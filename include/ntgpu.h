@@ -207,6 +207,10 @@ typedef struct ntg_tally_config {
     uint32_t has_query;        /* count canonical k-mers equal to `query` (lib.rs:31-35) */
     uint8_t query[64];         /* k ASCII bases ACGT                                     */
     uint32_t flags;            /* NTG_TALLY_* bits, 0 for normal use                     */
+    uint32_t qmask_score;      /* != 0 (FASTQ): QualitySequence::quality_mask(score) (src/sequence.rs:280-297) is applied to every
+                                  record before the loop above: a base whose quality byte is < score counts as 'N'.  Fused into
+                                  the record-owned short-read kernel (the quality line is resident beside its sequence line: no
+                                  extra DRAM traffic); other inputs are masked in a device copy first.  Not for stream sessions. */
 } ntg_tally_config;
 /* diagnostic: FASTQ tiles wait for the look-back instead of starting on the locally inferred line phase (same results) */
 #define NTG_TALLY_NO_SPECULATION 1u

@@ -69,7 +69,7 @@ class _Items(C.Structure):
 
 class _TallyConfig(C.Structure):
     _fields_ = [("k", C.c_uint32), ("m", C.c_uint32), ("allow_iupac", C.c_uint32), ("has_query", C.c_uint32),
-                ("query", C.c_uint8 * 64), ("flags", C.c_uint32)]
+                ("query", C.c_uint8 * 64), ("flags", C.c_uint32), ("qmask_score", C.c_uint32)]
 
 
 class _Tallies(C.Structure):
@@ -410,8 +410,8 @@ class Context:
     # ---- (3) fused hot path
     tally_flags = 0          # NTG_TALLY_* bits sent with every tally call (1 = no FASTQ line-phase speculation; diagnostic)
 
-    def _cfg(self, k, m, iupac, query):
-        cfg = _TallyConfig(k=k, m=m, allow_iupac=int(iupac), has_query=int(query is not None), flags=self.tally_flags)
+    def _cfg(self, k, m, iupac, query, qmask=0):
+        cfg = _TallyConfig(k=k, m=m, allow_iupac=int(iupac), has_query=int(query is not None), flags=self.tally_flags, qmask_score=qmask)
         if query is not None:
             q = bytes(query)
             for i, b in enumerate(q[:64]):
@@ -430,10 +430,10 @@ class Context:
                           "walker_wait": int(t.reserved[5]), "walker_work": int(t.reserved[6])}
         return d
 
-    def tally(self, data, k, m=0, iupac=False, query=None):
-        """Host bytes -> tallies dict (the end-to-end call: H2D inside) — ntg_tally_fastx"""
+    def tally(self, data, k, m=0, iupac=False, query=None, qmask=0):
+        """Host bytes -> tallies dict (the end-to-end call: H2D inside) — ntg_tally_fastx.  qmask: quality_mask(score) first."""
         arr = _as_u8(data)
-        cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
+        cfg = self._cfg(k, m, iupac, query, qmask); t = _Tallies(); e = _ParseError()
         self._ck(self.lib.ntg_tally_fastx(self.h, _ptr(arr), arr.size, C.byref(cfg), C.byref(t), C.byref(e)))
         return self._tally_result(t, e)
 
@@ -442,8 +442,8 @@ class Context:
         self._ck(self.lib.ntg_tally_fastx(self.h, host_ptr, nbytes, C.byref(cfg), C.byref(t), C.byref(e)))
         return self._tally_result(t, e)
 
-    def tally_device(self, dptr, nbytes, k, m=0, iupac=False, query=None):
-        cfg = self._cfg(k, m, iupac, query); t = _Tallies(); e = _ParseError()
+    def tally_device(self, dptr, nbytes, k, m=0, iupac=False, query=None, qmask=0):
+        cfg = self._cfg(k, m, iupac, query, qmask); t = _Tallies(); e = _ParseError()
         self._ck(self.lib.ntg_tally_fastx_device(self.h, dptr, nbytes, C.byref(cfg), C.byref(t), C.byref(e)))
         return self._tally_result(t, e)
 

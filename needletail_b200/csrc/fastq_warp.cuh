@@ -279,6 +279,15 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_records(const Params P) {
             }
             const int len = b - a;
             const int ap = a + (int)(((int64_t)len * part) / frags), bp = a + (int)(((int64_t)len * (part + 1)) / frags);
+            if (P.W.qmask) {
+                // QualitySequence::quality_mask (sequence.rs:280-297), fused: the record's quality line sits in the same buffer, so
+                // low-quality bases become 'N' in place before the walk (this lane owns the bytes; the two lanes of a split
+                // line write the same values where their ranges overlap).  Only the bases proper: trim_cr'd lengths.
+                const int nb = len - ((len > 0 && sb[b - 1] == '\r') ? 1 : 0);
+                const int q0 = (int)e2 + 1 - a;                             // offset from a base to its quality byte
+                const int from = max(a, ap - (int)P.W.k + 1), to = min(bp, a + nb);
+                for (int q = from; q < to; q++) if (sb[q + q0] < P.W.qmask) B.win[q] = 'N';
+            }
             run_fragment<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, ap, bp, P.W, acc, slow, mode);
         }
         __syncwarp();

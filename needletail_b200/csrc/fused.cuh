@@ -116,6 +116,7 @@ struct Params {
     uint64_t sp_mask;
     uint32_t* sp_overflow;
     uint32_t k, m, w;
+    uint32_t qmask;                    // != 0: bases whose quality byte is below it count as 'N' (record-owned FASTQ kernel only)
     uint32_t tile_bytes;               // multiple of 256, <= TILE: sized so one tile holds about NT sequence lines
     int format;                        // NTG_FMT_FASTA / NTG_FMT_FASTQ
     int has_query;

@@ -229,6 +229,7 @@ static int check_tally_cfg(ntg_ctx* ctx, const ntg_tally_config* cfg) {
     if (!cfg) return ntg_set_error(ctx, NTG_EINVAL, "null config");
     if (cfg->k == 0 || cfg->k > 64) return ntg_set_error(ctx, NTG_EINVAL, "k must be in 1..64");
     if (cfg->m && (cfg->k > 32 || cfg->m > cfg->k)) return ntg_set_error(ctx, NTG_EINVAL, "minimizers need 1 <= m <= k <= 32");
+    if (cfg->qmask_score > 255) return ntg_set_error(ctx, NTG_EINVAL, "qmask_score is a quality byte (0 = off, 1..255)");
     if (cfg->has_query)
         for (uint32_t i = 0; i < cfg->k; i++)
             if (host_luts().code[cfg->query[i]] > 3 || (cfg->query[i] & 0x20)) return ntg_set_error(ctx, NTG_EINVAL, "query must be k bases of ACGT");
@@ -277,6 +278,7 @@ static int fused_begin_pass(ntg_ctx* ctx, int format, const ntg_tally_config* cf
     P = fused::Params{};
     P.slots = st->slots; P.cw = st->cw; P.slot_mask = (1u << SLOT_SHIFT) - 1; P.slot_shift = SLOT_SHIFT; P.final_state = st->final_state;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
+    P.qmask = format == NTG_FMT_FASTQ ? (cfg->qmask_score & 0xFFu) : 0u;
     P.spec = (allow_spec && format == NTG_FMT_FASTQ && !(cfg->flags & NTG_TALLY_NO_SPECULATION)) ? 1 : 0;
     P.q_lo = P.q_hi = 0;
     if (cfg->has_query)
@@ -557,6 +559,8 @@ static int fq_tail(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_ta
     return NTG_OK;
 }
 
+static int tally_masked_copy(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, ntg_tallies* out, ntg_parse_error* err);
+
 // Whole-input tallies with the reference's iterator semantics.  `run(n_eff, mode, &result)` makes one pass over the first
 // n_eff bytes of the source (resident or streamed); every pass can be repeated because the caller still holds the bytes.
 template <typename Run>
@@ -566,12 +570,15 @@ static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const nt
     PassResult r;
     uint32_t spec_missed = 0;
     bool fq = false;
+    const bool qmask = cfg->qmask_score != 0 && format == NTG_FMT_FASTQ;
+    if (qmask && !fq_ok) return tally_masked_copy(ctx, src, format, cfg, out, err);       // (only the record-owned kernel masks in place)
     if (fq_ok) {
         // the record-owned fast path takes clean streams and streams whose only problem is a failing record; anything else
         // (a wrong phase guess, a record longer than its slack, a newline-dense chunk) is fused::k_fused's business
         NTG_TRY(run(src.n, MODE_FQ, &r));
         fq = r.flags == 0 || (r.flags == fused::FLAG_PARSE_ERROR && r.err_key != ~0ull);
     }
+    if (!fq && qmask) return tally_masked_copy(ctx, src, format, cfg, out, err);
     if (!fq) {
         NTG_TRY(run(src.n, MODE_SPEC, &r));
         if (r.flags & fused::FLAG_SPEC_MISS) { spec_missed = r.flags; NTG_TRY(run(src.n, MODE_NOSPEC, &r)); }   // a speculated FASTQ line phase was wrong
@@ -596,6 +603,7 @@ static int tally_whole(ntg_ctx* ctx, const ByteSource& src, int format, const nt
         if (E >= 2) {
             bool done = false;
             if (fq) { NTG_TRY(run(E, MODE_FQ, &t)); done = t.flags == 0 && t.fq_next >= E; }
+            if (!done && qmask) return tally_masked_copy(ctx, src, format, cfg, out, err);
             if (!done) {
                 NTG_TRY(run(E, MODE_SPEC, &t));
                 if (t.flags & fused::FLAG_SPEC_MISS) NTG_TRY(run(E, MODE_NOSPEC, &t));
@@ -677,6 +685,51 @@ static int exact_tally(ntg_ctx* ctx, const ByteSource& src, int format, const nt
     out->add(st->h_ctl[CTL_REDO]);
     out->flags = 0;
     return NTG_OK;
+}
+
+// quality_mask for inputs the record-owned kernel does not take (long reads, newline-dense files, a wrong phase guess): the text
+// is copied on the device, every delivered record's low-quality bases are overwritten with 'N' through the record table
+// (window by window), and the copy is tallied without the mask.
+namespace fused {
+__global__ void __launch_bounds__(128) k_mask_records(uint8_t* __restrict__ text, const ntg_record* __restrict__ recs, uint64_t n_recs, uint32_t score) {
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w >= n_recs) return;
+    const ntg_record r = recs[w];
+    const uint64_t n = r.seq_e - r.seq_b < r.qual_e - r.qual_b ? r.seq_e - r.seq_b : r.qual_e - r.qual_b;
+    for (uint64_t j = lane; j < n; j += 32) if (text[r.qual_b + j] < score) text[r.seq_b + j] = 'N';
+}
+}  // namespace fused
+static int tally_masked_copy(ntg_ctx* ctx, const ByteSource& src, int format, const ntg_tally_config* cfg, ntg_tallies* out, ntg_parse_error* err) {
+    DevBuf<uint8_t> copy;
+    if (copy.alloc(src.n + 16)) { cudaGetLastError(); return ntg_set_error(ctx, NTG_ENOMEM, "quality mask: no room for a device copy of %llu bytes", (unsigned long long)src.n); }
+    NTG_CUDA(ctx, cudaMemcpyAsync(copy.p, src.host ? (const void*)src.host : (const void*)src.dev, src.n, src.host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    uint64_t pos = 0, W = uint64_t(1) << 30;
+    while (pos < src.n) {
+        const uint64_t len = src.n - pos < W ? src.n - pos : W;
+        const bool at_eof = pos + len == src.n;
+        ntg_records* recs = nullptr; DevBuf<ntg_record> drecs; uint64_t consumed = 0;
+        NTG_TRY(run_parse_device(ctx, nullptr, copy.p + pos, (size_t)len, &recs, &drecs, format, at_eof, &consumed, nullptr));
+        const uint64_t nrec = recs->n_records; const bool stop = recs->error.kind != 0;
+        ntg_records_free(recs);
+        if (nrec) {
+            fused::k_mask_records<<<(unsigned)((nrec * 32 + 127) / 128), 128, 0, ctx->stream>>>(copy.p + pos, drecs.p, nrec, cfg->qmask_score);
+            ctx->launches++;
+            NTG_CUDA(ctx, cudaGetLastError());
+            NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // (the record table is freed at the end of this iteration)
+        }
+        if (stop || at_eof) break;                                   // (records behind the first error are never delivered: leave them alone)
+        if (consumed == 0) { if (W >= 0xF0000000ull) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "a record larger than 3.75 GiB"); W = W * 2 < 0xF0000000ull ? W * 2 : 0xF0000000ull; continue; }
+        pos += consumed;
+    }
+    ntg_tally_config plain = *cfg; plain.qmask_score = 0;
+    const uint8_t* d = copy.p;
+    std::vector<uint8_t> sample(src.n < 65536 ? src.n : 65536);
+    NTG_CUDA(ctx, cudaMemcpy(sample.data(), d, sample.size(), cudaMemcpyDeviceToHost));
+    const PassShape sh = pass_shape(sample.data(), sample.size(), format, &plain);
+    const ByteSource masked{nullptr, d, src.n, src.more_behind};
+    auto run = [&](uint64_t n_eff, int mode, PassResult* r) { return pass_resident(ctx, d, n_eff, format, &plain, sh, mode, r); };
+    return tally_whole(ctx, masked, format, &plain, sh.fq_ok, run, out, err);
 }
 
 static int sniff_format(ntg_ctx* ctx, uint8_t b0, size_t n, ntg_tallies* out, ntg_parse_error* err, int* format) {

@@ -313,6 +313,7 @@ int ntg_tally_fastx_device_enqueue(ntg_ctx* ctx, uint64_t dptr, size_t n, const 
     const uint64_t num_tiles = (n + tile_bytes - 1) / tile_bytes;
     const bool reduce = (cfg->flags & NTG_TALLY_ALLREDUCE) != 0;
     if (reduce && !ctx->nccl_comm) return ntg_set_error(ctx, NTG_EINVAL, "NTG_TALLY_ALLREDUCE needs ntg_comm_init");
+    if (cfg->qmask_score && format == NTG_FMT_FASTQ && !sh.fq_ok) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "quality masking of this input needs a masked copy: use ntg_tally_fastx_device");
     st->pending_fq = sh.fq_ok;
     if (sh.fq_ok) {
         // the record-owned fast path; collect falls back to the full logic when it reports anything but a clean, tail-less pass
@@ -402,6 +403,7 @@ int ntg_stream_open(ntg_ctx* ctx, const ntg_tally_config* cfg, ntg_stream** out)
     if (!out) return ntg_set_error(ctx, NTG_EINVAL, "null output");
     *out = nullptr;
     if (cfg && (cfg->flags & NTG_TALLY_ALLREDUCE)) return ntg_set_error(ctx, NTG_EINVAL, "NTG_TALLY_ALLREDUCE is for the enqueue/collect form");
+    if (cfg && cfg->qmask_score) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "quality masking is not available in stream sessions: use ntg_tally_fastx");
     if (ctx->fused && ctx->fused->pending) return ntg_set_error(ctx, NTG_EINVAL, "a tally call is pending: collect it first");
     return stream_create(ctx, cfg, out);
 }

@@ -512,3 +512,40 @@ def test_record_writers(ctx, fixtures):  # src/parser/record.rs:158-247, tests a
     p = ctx.parse(fq)
     back = ctx.parse(ctx.write_records(fq, p))
     assert [r.seq for r in back.records] == [r.seq for r in p.records] and [r.qual for r in back.records] == [r.qual for r in p.records]
+
+
+def test_quality_mask_fused_into_the_tally(ctx, fixtures):  # src/sequence.rs:280-297 applied before the per-record loop
+    rng = random.Random(53)
+
+    def masked_text(data, score):
+        out = bytearray(data)
+        for row in O.parse_fastx(bytes(data)).table:
+            sb, se, qb, qe = (int(row[i]) for i in (3, 4, 5, 6))
+            for j in range(min(se - sb, qe - qb)):
+                if data[qb + j] < score:
+                    out[sb + j] = ord("N")
+        return bytes(out)
+
+    cases = [(O.gen_fastq(0x5EED0002, 0, 3000, 150, 200).tobytes(), True), (fixtures["data/PRJNA271013_head.fq"], None),
+             (mutate_fastq(rng, 1500, 120, crlf=True), None),
+             (b"@long\n" + bytes(rng.choice(b"ACGT") for _ in range(9000)) + b"\n+\n" + bytes(rng.randrange(33, 75) for _ in range(9000)) + b"\n", False)]
+    for data, fast in cases:
+        for score in (34, 50, 74):
+            want_text = masked_text(data, score)
+            for k, m in ((31, 21), (15, 9)):
+                exp = O.tally_fastx(want_text, k=k, m=m)
+                got = ctx.tally(data, k=k, m=m, qmask=score)
+                for key in TALLY_KEYS:
+                    assert got[key] == exp[key], (score, k, key, got[key], exp[key])
+                if fast is not None:
+                    assert got["fast_path"] == fast
+        plain = ctx.tally(data, k=31, m=21)
+        assert plain["n_kmers"] >= ctx.tally(data, k=31, m=21, qmask=60)["n_kmers"]
+    # errors keep their semantics under the mask; FASTA ignores it (no quality)
+    fq = cases[0][0]
+    bad = fq[: 316 * 900] + b"X" + fq[316 * 900 + 1:]
+    got = ctx.tally(bad, k=31, m=21, qmask=50)
+    exp = O.tally_fastx(masked_text(bad[: 316 * 900], 50), k=31, m=21)
+    assert got["err_kind"] == "InvalidStart" and got["n_records"] == 900 and got["kmer_sum_lo"] == exp["kmer_sum_lo"]
+    fa = fixtures["data/28S.fasta"]
+    assert ctx.tally(fa, k=31, qmask=50)["kmer_sum_lo"] == ctx.tally(fa, k=31)["kmer_sum_lo"]

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import needletail_b200 as nt
     assert C.sizeof(nt._Record) == 80 and C.sizeof(nt._Tallies) == 128
-    assert C.sizeof(nt._TallyConfig) == 84 and C.sizeof(nt._ParseError) == 264
+    assert C.sizeof(nt._TallyConfig) == 88 and C.sizeof(nt._ParseError) == 264
 
 
 def test_no_cpu_fallback():
