@@ -102,7 +102,7 @@ class ClockSampler:
 def cpu_baseline(L, k, m, budget_cpu_s=20.0, max_bytes=4 << 30):
     """Time the oracle (the reference's per-record loop, restated) on all host cores over a bounded sample."""
     import oracle_lib as O
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)      # the cores this process may use
     rb = 2 * L + 16
     probe = O.gen_fastq(SEED, 0, 20000, L, 0, nthreads=min(cores, 8))
     _, secs = O.bench_fastq(probe, rb, 1, k, m)
@@ -121,6 +121,25 @@ def cpu_baseline(L, k, m, budget_cpu_s=20.0, max_bytes=4 << 30):
             "single_thread_value": rate1 / 1e9}, t
 
 
+def cpu_baseline_fasta(L, k, m, seed, budget_s=15.0):
+    """FASTA shapes: the oracle's whole-input loop (ntref_tally_fastx) on one shard per host thread (ctypes drops the GIL)."""
+    import oracle_lib as O
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    t0 = time.perf_counter(); O.tally_fastx(O.gen_fasta(seed, 0, 20, L, 0).tobytes(), k=k, m=m); one = time.perf_counter() - t0
+    nrec = max(4, int(budget_s / 3 / max(one / 20, 1e-9)))
+    shards = [O.gen_fasta(seed, i * nrec, nrec, L, 0).tobytes() for i in range(cores)]
+    best = None
+    for _ in range(2):
+        ths = [threading.Thread(target=O.tally_fastx, args=(sh,), kwargs=dict(k=k, m=m)) for sh in shards]
+        t0 = time.perf_counter()
+        for t in ths: t.start()
+        for t in ths: t.join()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": cores * nrec * L / best / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} x {nrec} records x {L} bp of synthetic FASTA, one shard per host thread, best of 2, C++ oracle of the reference loop"}, None
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     rank = env_int("RANK", 0)
@@ -128,7 +147,7 @@ def run_reference(args):
         return
     import oracle_lib as O
     L, k, m = args.read_len, args.k, args.m
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rb = 2 * L + 16
     # size one step from a short all-threads probe so that the whole --steps/--warmup run takes about 90 s
     nprobe = cores * 4000
@@ -160,26 +179,33 @@ def run_reference(args):
     })
 
 
-def verify_full_scale(ctx, dbuf, nrec, rec0, L, k, m, full, n_thresh=0):
+def rec_bytes(L, fmt):
+    return 2 * L + 16 if fmt == "fastq" else L + 12
+
+
+def verify_full_scale(ctx, dbuf, nrec, rec0, L, k, m, full, n_thresh=0, fmt="fastq", seed=SEED):
     """Checks, outside the timed region, that the tallies of the whole resident shard are right — not only its counts:
     (1) the oracle (CPU) on sampled sub-shards of the very bytes resident in HBM, against the kernel on the same sub-shards;
     (2) the whole-shard tallies equal the sum over a partition into 7 parts (other tile alignments, other look-back chains).
     Checksums are wrapping u64 sums, so both properties are exact."""
     import numpy as np
     import oracle_lib as O
-    rb = 2 * L + 16
+    rb = rec_bytes(L, fmt)
+    gen = O.gen_fastq if fmt == "fastq" else O.gen_fasta
     keys = ("n_records", "n_bases", "n_kmers", "n_not_rc", "kmer_sum_lo", "n_minimizers", "minimizer_sum")
-    sub = 20_000
-    starts = sorted({(nrec - sub) * i // 4 // 4 * 4 for i in range(5)}) if nrec > sub else [0]      # 4-record steps keep 16 B alignment
+    sub = 20_000 if fmt == "fastq" else 400
+    step4 = 4 if fmt == "fastq" else 16                          # record steps that keep sub-shards 16-byte aligned
+    assert (rb * step4) % 16 == 0
+    starts = sorted({(nrec - sub) * i // 4 // step4 * step4 for i in range(5)}) if nrec > sub else [0]
     for r0 in starts:
         n = min(sub, nrec - r0)
         got = ctx.tally_device(dbuf + r0 * rb, n * rb, k=k, m=m)
-        exp = O.tally_fastx(O.gen_fastq(SEED, rec0 + r0, n, L, n_thresh).tobytes(), k=k, m=m)
+        exp = O.tally_fastx(gen(seed, rec0 + r0, n, L, n_thresh).tobytes(), k=k, m=m)
         for key in keys:
             assert got[key] == exp[key], ("oracle sample", r0, key, got[key], exp[key])
     parts, acc = 7, {key: 0 for key in keys}
     for i in range(parts):
-        a, b = nrec * i // parts // 4 * 4, (nrec * (i + 1) // parts // 4 * 4 if i + 1 < parts else nrec)
+        a, b = nrec * i // parts // step4 * step4, (nrec * (i + 1) // parts // step4 * step4 if i + 1 < parts else nrec)
         t = ctx.tally_device(dbuf + a * rb, (b - a) * rb, k=k, m=m)
         assert t["err_kind"] is None and t["fallback"] == 0
         for key in keys:
@@ -275,13 +301,13 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return
-    L, k, m = args.read_len, args.k, args.m
-    rb = 2 * L + 16
+    L, k, m, fmt, seed = args.read_len, args.k, args.m, args.format, args.seed
+    rb = rec_bytes(L, fmt)
     total_rec = args.reads                              # strong scaling: the named shape is split over the ranks
     rec0, nrec = shard.shard_records(total_rec, world, rank)
     nbytes = nrec * rb
     dbuf = ctx.device_alloc(nbytes)
-    ctx.synth_fastq_device(dbuf, SEED, rec0, nrec, L, args.n_thresh)
+    (ctx.synth_fastq_device if fmt == "fastq" else ctx.synth_fasta_device)(dbuf, seed, rec0, nrec, L, args.n_thresh)
     ctx.sync()
 
     def barrier():
@@ -332,7 +358,7 @@ def run_ours(args):
     verified = None
     if not args.no_verify:
         local_t = ctx.tally_device(dbuf, nbytes, k=k, m=m)
-        verified = verify_full_scale(ctx, dbuf, nrec, rec0, L, k, m, local_t, args.n_thresh)
+        verified = verify_full_scale(ctx, dbuf, nrec, rec0, L, k, m, local_t, args.n_thresh, fmt, seed)
         if world > 1:
             summed = shard.allreduce_tallies({f: local_t[f] for f in nt.TALLY_FIELDS}, ctx)     # host-staged reduce of the same shards
             for f in nt.TALLY_FIELDS:
@@ -344,7 +370,8 @@ def run_ours(args):
     achieved = nbytes / (kavg * 1e-3) / 1e9
     ratio = load_traffic_ratio()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ratio * nbytes) if ratio else None, "kernel": "fqw::k_records<1,true,11,31,21> (+ k_verify, fix-up launch)", "kernel_ms": kavg,
+                "traffic": (ratio * nbytes) if ratio else None,
+                "kernel": "fqw::k_records (+ k_verify, fix-up launch)" if tallies.get("fast_path") else "fused::k_fused", "kernel_ms": kavg,
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "traffic_note": "DRAM bytes per launch = ncu dram read+write bytes per input byte (profiles/traffic.json) x algorithmic bytes",
                 "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~41 SASS thread-instructions per base, ~25 of them on the 16-lane INT pipe, which is 84 % busy in the record-owned kernel (ncu profiles/r2h_*; 63 % in the tile kernel it replaces for short-read FASTQ); see DESIGN.md"}
@@ -389,15 +416,15 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = cpu_baseline(L, k, m)
+        cpu, _ = cpu_baseline(L, k, m) if fmt == "fastq" else cpu_baseline_fasta(L, k, m, seed)
     if dist is not None:
         dist.barrier()
     if rank == 0:
         emit({
-            "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": args.metric, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {total_rec} x {L}bp FASTQ ({total_rec * rb / 1e9:.1f} GB text) split over {world} GPU(s), resident in HBM, "
+            "config": {"workload": f"{args.config}: synthetic {total_rec} x {L}bp {fmt.upper()} ({total_rec * rb / 1e9:.1f} GB text) split over {world} GPU(s), resident in HBM, "
                                    f"k={k} canonical k-mers + m={m} minimizers, tallies" + (f", N bases at {args.n_thresh}/65536" if args.n_thresh else ""),
                        "k": k, "m": m, "w": k - m + 1, "read_len": L, "reads_per_gpu": nrec,
                        "l2": f"input per GPU ({nbytes / 1e9:.1f} GB) >> L2 (126 MB): no flush needed",
@@ -448,7 +475,21 @@ def main():
     ap.add_argument("--n-thresh", type=int, default=0, help="N bases: threshold / 65536 per base (655 = 1 %%, BASELINE config C4)")
     ap.add_argument("--workload", default="resident", choices=["resident", "gz"], help="gz: the compressed-input pipeline (BASELINE config C5 shape)")
     ap.add_argument("--gz-threads", type=int, default=-1, help="-1: host cores / ranks; 0: inflate on the device; n: n host threads")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configs at their named sizes: C2 (default, the headline), C3 10M x 10kbp FASTA k=21 m=11, "
+                         "C4 = C2 with 1 %% N, C5 = BGZF 50M x 250bp k=51 through the inflate pipeline")
     args = ap.parse_args()
+    args.format, args.seed, args.metric = "fastq", SEED, METRIC
+    if args.config == "C3":
+        args.format, args.seed, args.reads, args.read_len, args.k, args.m = "fasta", 0x5EED0003, 10_000_000, 10_000, 21, 11
+        args.metric = "Gbases/s k=21 bit k-mers + w=11 minimizers over 10M x 10kbp FASTA"
+    elif args.config == "C4":
+        args.n_thresh, args.seed = 655, 0x5EED0004
+        args.metric = METRIC + " with 1% N bases"
+    elif args.config == "C5":
+        args.workload, args.reads, args.read_len, args.k, args.m = "gz", 50_000_000, 250, 51, 0
+        if args.gz_threads < 0:
+            args.gz_threads = 0                                  # inflate on the device
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)          # timing hygiene: at least three untimed passes
     quiet_stdout()

@@ -424,10 +424,11 @@ class Context:
         d["err_kind"] = ERROR_KINDS.get(e.kind) if e.kind else None
         d["err_line"] = int(e.line)
         d["fallback"] = int(t.reserved[0]) & 0xFFFFFFFF      # 0: the single-pass fused kernel produced the tallies
-        d["ws_handover"] = int(t.reserved[1]) & 0xFFFFFFFF   # != 0: a speculated FASTQ line phase was wrong and the pass re-ran without speculation
+        d["spec_missed"] = int(t.reserved[1]) & 0xFFFFFFFF   # != 0: a speculated FASTQ line phase was wrong and the pass re-ran without speculation
         d["fast_path"] = bool(int(t.reserved[1]) >> 32)       # the record-owned short-read FASTQ kernel produced the tallies
-        d["ws_cycles"] = {"claim": int(t.reserved[2]), "scan": int(t.reserved[3]), "lookback_retry": int(t.reserved[4]),
-                          "walker_wait": int(t.reserved[5]), "walker_work": int(t.reserved[6])}
+        # NTG_STATS builds of the tile kernel only (per-CTA cycle accounting, see fused.cuh); zero otherwise
+        d["stats"] = {"cta_cycles_sum": int(t.reserved[2]), "p0_or_lookback_cycles": int(t.reserved[3]), "p1_cycles_or_lookbacks": int(t.reserved[4]),
+                      "barrier_wait_cycles_t0": int(t.reserved[5]), "walk_cycles_t0": int(t.reserved[6])}
         return d
 
     def tally(self, data, k, m=0, iupac=False, query=None, qmask=0):

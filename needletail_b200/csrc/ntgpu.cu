@@ -354,10 +354,11 @@ int ntg_tally_fastx_device_collect(ntg_ctx* ctx, ntg_tallies* out, ntg_parse_err
         if (st->h_reduce[9] == 0) {
             PassResult r; for (int i = 0; i < 9; i++) r.tallies[i] = st->h_reduce[i];
             tallies_from_pass(r, out);
+            if (st->pending_fq) out->reserved[1] |= NTG_RESERVED_FAST_PATH;
             return NTG_OK;
         }
-        if (clean) { PassResult r; r.add(c); tallies_from_pass(r, out); out->reserved[0] = NTG_RESERVED_NOT_REDUCED; return NTG_OK; }
-    } else if (clean) { PassResult r; r.add(c); tallies_from_pass(r, out); return NTG_OK; }
+        if (clean) { PassResult r; r.add(c); tallies_from_pass(r, out); out->reserved[0] = NTG_RESERVED_NOT_REDUCED; if (st->pending_fq) out->reserved[1] |= NTG_RESERVED_FAST_PATH; return NTG_OK; }
+    } else if (clean) { PassResult r; r.add(c); tallies_from_pass(r, out); if (st->pending_fq) out->reserved[1] |= NTG_RESERVED_FAST_PATH; return NTG_OK; }
     if (c.flags & fused::FLAG_FORMAT) st->sniff_format = 0;          // the buffer changed format since it was sniffed
     ntg_tally_config cfg = st->cfg; cfg.flags &= ~NTG_TALLY_ALLREDUCE;
     const int rc = tally_resident(ctx, st->pend_dptr, st->pend_n, &cfg, out, err);

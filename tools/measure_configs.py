@@ -75,10 +75,8 @@ def main():
         out.append({"config": name, "bytes": nbytes, "kernel_ms": avg, "gbases_per_s": reads * L / avg / 1e6,
                     "gb_per_s": nbytes / avg / 1e6, "n_kmers": t["n_kmers"], "n_not_rc": t["n_not_rc"],
                     "kmer_sum_lo": t["kmer_sum_lo"], "kmer_sum_hi": t["kmer_sum_hi"], "minimizer_sum": t["minimizer_sum"]})
-        if any(t["ws_cycles"].values()):          # NTG_STATS build: per-CTA cycle accounting (see fused.cuh)
-            c = t["ws_cycles"]
-            out[-1]["stats"] = {"cta_cycles_sum": c["claim"], "lookback_cycles": c["scan"], "lookbacks": c["lookback_retry"],
-                                "barrier_wait_cycles_t0": c["walker_wait"], "walk_cycles_t0": c["walker_work"], "n_query_slot": t["n_query"]}
+        if any(t["stats"].values()):              # NTG_STATS build: per-CTA cycle accounting (see fused.cuh)
+            out[-1]["stats"] = dict(t["stats"], n_query_slot=t["n_query"])
         print(json.dumps(out[-1]), flush=True)
     ctx.close()
 
