@@ -290,7 +290,7 @@ class Context:
         self._ck(self.lib.ntg_write_records(*args, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value].tobytes()
 
-    def parse_chunks(self, data, window=1 << 30):
+    def parse_chunks(self, data, window=1 << 30, with_records=True):
         """Generator of Parsed, one per window of `window` bytes (< 4 GiB) — ntg_parse_fastx_chunk: the incremental reader behind
         FastxReader for inputs of any size.  Offsets, lines and error positions are made absolute; the last Parsed carries
         the end-of-stream error, if any."""
@@ -303,7 +303,7 @@ class Context:
             win = arr[pos:pos + ln]
             self._ck(self.lib.ntg_parse_fastx_chunk(self.h, _ptr(win), ln, fmt, int(at_eof), C.byref(out), C.byref(consumed)))
             try:
-                p = Parsed(win, out.contents)
+                p = Parsed(win, out.contents, with_records)
             finally:
                 self.lib.ntg_records_free(out)
             fmt = {"fasta": 1, "fastq": 2}.get(p.format, 0)
@@ -693,13 +693,13 @@ class Record:
 
 
 class Parsed:
-    def __init__(self, data, rs):
+    def __init__(self, data, rs, with_records=True):
         self.format = FORMATS[rs.format]
         self.line_ending = LINE_ENDINGS[rs.line_ending]
         self.final_line, self.final_byte = int(rs.final_line), int(rs.final_byte)
         n = int(rs.n_records)
         self.table = np.ctypeslib.as_array(C.cast(rs.records, C.POINTER(C.c_uint64)), shape=(n, 10)).copy() if n else np.zeros((0, 10), np.uint64)
-        self.records = [Record._from_table(data, rs.records[i], self.format) for i in range(n)]
+        self.records = [Record._from_table(data, rs.records[i], self.format) for i in range(n)] if with_records else []
         e = rs.error
         self.err_kind = ERROR_KINDS.get(e.kind) if e.kind else None
         self.err_line = int(e.line)
