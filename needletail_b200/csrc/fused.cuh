@@ -108,6 +108,7 @@ struct Params {
     unsigned long long* fin;           // k_finalize: [0] error kind of an end-of-stream error, [1] its line (FASTA)
     unsigned long long* reduce_buf;    // non-null: k_finalize copies the tallies (+ a "needs the host" count) into the all-reduce send buffer
     SState* final_state;
+    unsigned long long* fa_totals;     // FASTA: [0] record starts, [1] newlines of the whole pass (sums; the look-back carries the header state only)
     // k-mer spectrum passes (spectrum.cuh): every canonical k-mer the generic walker tallies is also counted, in a dense
     // histogram (k <= 14: 4^k counters) or in an open-addressing hash table (keys ~0 = empty)
     uint32_t* sp_dense;
@@ -729,15 +730,11 @@ __host__ __device__ __forceinline__ bool walk_clean2(const uint8_t* __restrict__
 }
 
 // =============================================================================== look-back
-__device__ __forceinline__ SState shfl_state(const SState& v, int src) {
-    SState r;
-    r.count = __shfl_sync(0xffffffffu, v.count, src);
-#pragma unroll
-    for (int i = 0; i < 4; i++) r.last[i] = __shfl_sync(0xffffffffu, v.last[i], src);
-    r.n_starts = __shfl_sync(0xffffffffu, v.n_starts, src);
-    r.hdr = __shfl_sync(0xffffffffu, v.hdr, src);
-    r.first_nl = __shfl_sync(0xffffffffu, v.first_nl, src);
-    return r;
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // ---- the ring of tile slots ---------------------------------------------------------------
 // Tile t uses slot t & slot_mask; its flag / look-back word carries the generation epoch + (t >> slot_shift), so a slot that
@@ -745,35 +742,89 @@ __device__ __forceinline__ SState shfl_state(const SState& v, int src) {
 __device__ __forceinline__ TileSlot* slot_of(const Params& P, uint64_t t) { return &P.slots[t & P.slot_mask]; }
 __device__ __forceinline__ uint32_t epoch_of(const Params& P, uint32_t epoch, uint64_t t) { return (epoch + (uint32_t)(t >> P.slot_shift)) & 0x3FFFFFFFu; }
 
-// Exclusive prefix of tile t (general state: FASTA), computed by one whole warp: lane l inspects tile base-l, so 32
-// predecessors are examined per step (a serial walk makes look-backs slow, which lengthens the window of tiles that have
-// only published aggregates, which makes look-backs slower still).
-__device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
-    SState suffix = identity_state();
+// ---- FASTA look-back on one 64-bit word per tile (round 2) ---------------------------------------------------------------
+// What a FASTA tile needs from everything before it is the header state only: does it start inside a header line, and where did
+// the newest header line end (the start of the current sequence region).  Record starts and newlines are plain sums and go to
+// Params::fa_totals.  combine(a, b) on that state: b's header event if it has one; else, if a ends inside a header, that header
+// ends at b's first newline (or still has not ended); else a's.  So a tile publishes ONE word — generation << 34 | state << 32
+// | kind << 30 | offset — first its aggregate (state 1: kind 0 nothing, 1 first newline at `offset`, 2 newest header ended at
+// `offset`, 3 ends inside a header; offsets are tile-relative), later the inclusive prefix (state 2: kind 0 no header yet,
+// 2 newest header ended `offset` bytes before the END of the tile (saturating: only distances up to the halo matter), 3 inside a
+// header).  A look-back step is one relaxed load per predecessor, 128 predecessors per step, and a shuffle tree over
+// (kind, position) pairs — instead of 256-byte slots and a tree over eight 64-bit fields per predecessor, which cost the
+// 10 kbp FASTA shape half of every CTA's time (NTG_STATS, profiles/r2a_*).
+constexpr int LBQ_G = 4;                            // predecessors per lane and look-back step
+constexpr uint32_t FA_OFF_BITS = 30;
+constexpr uint64_t FA_FAR = (1ull << FA_OFF_BITS) - 1;
+struct FaState { uint32_t kind; int64_t pos; };                    // pos: stream position (kind 1: first newline, kind 2: header-ending newline)
+__host__ __device__ __forceinline__ FaState fa_combine(const FaState& a, const FaState& b) {          // a = earlier span, b = later span
+    // aggregate semantics: kind 0 = no event, no newline; 1 = no header event, first newline at pos; 2 = header ended at pos; 3 = ends in a header
+    // (an inclusive prefix never has kind 1: folded against what precedes it a bare newline is no event)
+    if (b.kind >= 2) return b;
+    if (a.kind == 3) return b.kind == 1 ? FaState{2u, b.pos} : FaState{3u, 0};
+    if (a.kind == 2) return a;
+    return b.kind == 1 && a.kind == 1 ? a : (a.kind ? a : b);      // no header event on either side: keep the EARLIEST first newline
+}
+// the header state of a span as the look-back word carries it (SState::hdr / first_nl -> kind, position)
+__host__ __device__ __forceinline__ FaState fa_of(const SState& s) {
+    if (s.hdr == INHDR) return FaState{3u, 0};
+    if (s.hdr != NONE) return FaState{2u, (int64_t)s.hdr};
+    if (s.first_nl != NONE) return FaState{1u, (int64_t)s.first_nl};
+    return FaState{0u, 0};
+}
+__device__ __forceinline__ unsigned long long fa_word(uint32_t gen, uint32_t state, uint32_t kind, uint64_t off) {
+    return ((unsigned long long)gen << 34) | ((unsigned long long)state << 32) | ((unsigned long long)kind << FA_OFF_BITS) | (off < FA_FAR ? off : FA_FAR);
+}
+// header state in front of tile t (t > 0) as an SState whose hdr field is NONE / INHDR / the stream position of the newest
+// header-ending newline (a position farther back than FA_FAR bytes comes back as "FA_FAR before the tile": beyond any halo)
+__device__ __forceinline__ SState fasta_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
+    const int64_t TB = (int64_t)P.tile_bytes;
+    FaState suffix{0u, 0};
     int64_t base = (int64_t)t - 1;
-    uint32_t backoff = 32;                                          // ns; doubles up to 256 (polling costs issue slots and L2 traffic)
+    uint32_t backoff = 32;
     for (;;) {
-        const int64_t j = base - (int64_t)lane;
-        uint32_t st = 2;                                            // before the first tile: inclusive(identity)
-        if (j >= 0) { const uint32_t f = ld_acquire_u32(&slot_of(P, (uint64_t)j)->flag); st = ((f >> 2) == epoch_of(P, epoch, (uint64_t)j)) ? (f & 3u) : 0u; }
-        const uint32_t inc_mask = __ballot_sync(0xffffffffu, st == 2), nr_mask = __ballot_sync(0xffffffffu, st == 0);
+        const int64_t j0 = base - (int64_t)lane * LBQ_G;
+        unsigned long long w[LBQ_G];
+#pragma unroll
+        for (int g = 0; g < LBQ_G; g++) { const int64_t j = j0 - g; w[g] = j >= 0 ? ld_relaxed_u64(&P.cw[(uint64_t)j & P.slot_mask]) : 0ull; }
+        FaState mine{0u, 0};
+        uint32_t lane_state = 0;                                    // 0: G aggregates folded, 1: reached an inclusive prefix, 2: blocked
+#pragma unroll
+        for (int g = 0; g < LBQ_G; g++) {
+            const int64_t j = j0 - g;
+            uint32_t st = 2, kind = 0; int64_t pos = 0;             // before the first tile: inclusive(nothing)
+            if (j >= 0) {
+                st = ((uint32_t)(w[g] >> 34) == epoch_of(P, epoch, (uint64_t)j)) ? (uint32_t)(w[g] >> 32) & 3u : 0u;
+                kind = (uint32_t)(w[g] >> FA_OFF_BITS) & 3u;
+                const int64_t off = (int64_t)(w[g] & FA_FAR);
+                pos = st == 2 ? (j + 1) * TB - off : j * TB + off;   // inclusive: distance back from the tile's end; aggregate: tile-relative
+            }
+            if (lane_state == 0) {
+                if (st == 0) lane_state = 2;
+                else { mine = fa_combine(FaState{kind, pos}, mine); if (st == 2) lane_state = 1; }
+            }
+        }
+        const uint32_t inc_mask = __ballot_sync(0xffffffffu, lane_state == 1), blk_mask = __ballot_sync(0xffffffffu, lane_state == 2);
         const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
         const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if (nr_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
+        if (blk_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
         const int top = first_inc < 32 ? first_inc : 31;
-        SState acc = identity_state();                              // lanes above `top` contribute the identity
-        if (j >= 0 && (int)lane <= top) acc = ((int)lane == first_inc) ? slot_of(P, (uint64_t)j)->inc : slot_of(P, (uint64_t)j)->agg;
-        // ordered tree reduction: lane l holds tile base-l, higher lanes are EARLIER tiles; combine() is associative
+        FaState acc = (int)lane <= top ? mine : FaState{0u, 0};      // lanes above `top` contribute the identity
+        // ordered tree reduction: lane l holds the tiles base-4l ..; higher lanes are EARLIER tiles
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const SState earlier = shfl_state(acc, (int)lane + d < 32 ? (int)lane + d : (int)lane);
-            if ((int)lane + d < 32) acc = combine(earlier, acc);
+            const int src = (int)lane + d < 32 ? (int)lane + d : (int)lane;
+            FaState e; e.kind = __shfl_sync(0xffffffffu, acc.kind, src); e.pos = __shfl_sync(0xffffffffu, acc.pos, src);
+            if ((int)lane + d < 32) acc = fa_combine(e, acc);
         }
-        acc = shfl_state(acc, 0);
-        suffix = combine(acc, suffix);
-        if (first_inc < 32) return suffix;
-        base -= 32;
+        acc.kind = __shfl_sync(0xffffffffu, acc.kind, 0); acc.pos = __shfl_sync(0xffffffffu, acc.pos, 0);
+        suffix = fa_combine(acc, suffix);
+        if (first_inc < 32) break;
+        base -= 32 * LBQ_G;
     }
+    SState pre = identity_state();
+    pre.hdr = suffix.kind == 3 ? INHDR : (suffix.kind == 2 ? (uint64_t)suffix.pos : NONE);
+    return pre;
 }
 
 // ---- FASTQ look-back on one 64-bit word per tile (round 2) ------------------------------------------------------
@@ -786,7 +837,6 @@ __device__ __forceinline__ SState warp_lookback(const Params& P, uint64_t t, uin
 // The r1 look-back of the headline run took 33 000 cycles per tile (NTG_STATS) and the tile loop ran 12 % faster without it.
 // The positions of the last four newlines before a tile (line lengths of the lines that cross into it) come from the
 // aggregates of its nearest predecessors (collect_last).
-constexpr int LBQ_G = 4;
 __host__ __device__ __forceinline__ uint32_t enc_count(uint64_t c) { return (uint32_t)(c & 3u) | (c >= 4 ? 4u : 0u); }
 __host__ __device__ __forceinline__ uint32_t enc_combine(uint32_t a, uint32_t b) {
     const uint32_t s = (a & 3u) + (b & 3u);
@@ -794,12 +844,6 @@ __host__ __device__ __forceinline__ uint32_t enc_combine(uint32_t a, uint32_t b)
 }
 __device__ __forceinline__ unsigned long long cw_make(uint32_t gen, uint32_t state, uint32_t enc) {
     return ((unsigned long long)gen << 34) | ((unsigned long long)state << 32) | enc;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-    unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // encoded exclusive prefix of tile t (t > 0); whole warp.  Ends with a fence: the aggregates of every predecessor are visible.
 __device__ __forceinline__ uint32_t fastq_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
@@ -855,7 +899,7 @@ __device__ __forceinline__ void collect_last(const Params& P, uint64_t t_excl, u
 __device__ __forceinline__ SState tile_prefix(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, bool fasta, uint32_t& slow) {
     SState pre = identity_state();
     if (t == 0) return pre;
-    if (fasta) return warp_lookback(P, t, epoch, lane);
+    if (fasta) return fasta_lookback(P, t, epoch, lane);
     pre.count = fastq_lookback(P, t, epoch, lane);
     if (lane == 0) collect_last(P, t, pre.last, 0, slow);
 #pragma unroll
@@ -864,20 +908,30 @@ __device__ __forceinline__ SState tile_prefix(const Params& P, uint64_t t, uint3
 }
 // one thread: make the tile's aggregate visible to the look-backs of its successors
 __device__ __forceinline__ void publish_aggregate(const Params& P, uint64_t t, uint32_t epoch, const SState& agg, bool fasta) {
+    if (fasta) {
+        // header state of the tile alone (see fasta_lookback); the sums go to the pass totals
+        const uint64_t ts = t * (uint64_t)P.tile_bytes;
+        uint32_t kind = 0; uint64_t off = 0;
+        if (agg.hdr == INHDR) kind = 3;
+        else if (agg.hdr != NONE) { kind = 2; off = agg.hdr - ts; }
+        else if (agg.first_nl != NONE) { kind = 1; off = agg.first_nl - ts; }
+        st_release_u64(&P.cw[t & P.slot_mask], fa_word(epoch_of(P, epoch, t), 1, kind, off));
+        if (agg.n_starts) atomicAdd(&P.fa_totals[0], (unsigned long long)agg.n_starts);
+        if (agg.count) atomicAdd(&P.fa_totals[1], (unsigned long long)agg.count);
+        return;
+    }
     TileSlot* slot = slot_of(P, t);
     slot->agg = agg;
-    if (fasta) { __threadfence(); st_release_u32(&slot->flag, epoch_of(P, epoch, t) * 4 + 1); }
-    else st_release_u64(&P.cw[t & P.slot_mask], cw_make(epoch_of(P, epoch, t), 1, enc_count(agg.count)));
+    st_release_u64(&P.cw[t & P.slot_mask], cw_make(epoch_of(P, epoch, t), 1, enc_count(agg.count)));
 }
 // one thread: publish the inclusive prefix of tile t (and hand the stream's final state to k_finalize)
 __device__ __forceinline__ void publish_inclusive(const Params& P, uint64_t t, uint32_t epoch, const SState& pre, const SState& agg, bool fasta) {
     SState inc;
     if (fasta) {
-        TileSlot* slot = slot_of(P, t);
-        inc = combine(pre, agg);
-        slot->inc = inc;
-        __threadfence();
-        st_release_u32(&slot->flag, epoch_of(P, epoch, t) * 4 + 2);
+        inc = combine(pre, agg);                                   // (only hdr is meaningful: pre carries nothing else)
+        const uint64_t te = (t + 1) * (uint64_t)P.tile_bytes;
+        const uint32_t kind = inc.hdr == INHDR ? 3u : (inc.hdr != NONE ? 2u : 0u);
+        st_release_u64(&P.cw[t & P.slot_mask], fa_word(epoch_of(P, epoch, t), 2, kind, kind == 2 ? te - inc.hdr : 0));
     } else {
         inc = identity_state();
         inc.count = enc_combine((uint32_t)pre.count, enc_count(agg.count));
@@ -1511,12 +1565,13 @@ __global__ void k_finalize(const Params P) {
         // FASTA: the last record needs a pushed newline (one that is not the final byte); without one it is an UnexpectedEnd
         // (fasta.rs:205-213,348-356) and is not delivered.  Its header line is the last line of the stream: nothing of it was tallied.
         const bool bad = st.hdr == INHDR || st.hdr == NONE || st.hdr == P.n - 1;
-        P.tallies[0] = st.n_starts - (bad && st.n_starts ? 1 : 0);
+        const uint64_t n_starts = P.fa_totals[0], count = P.fa_totals[1];           // sums over every tile of the pass
+        P.tallies[0] = n_starts - (bad && n_starts ? 1 : 0);
         if (bad) {
             slow |= FLAG_PARSE_ERROR;
             P.fin[0] = NTG_EUNEXPECTED_END;
-            P.fin[1] = 1 + st.count - ((st.hdr != INHDR && st.hdr != NONE) ? 1 : 0);    // line of that header: newlines before it + 1
-            P.fin[2] = st.n_starts ? st.n_starts - 1 : 0;                              // its record index
+            P.fin[1] = 1 + count - ((st.hdr != INHDR && st.hdr != NONE) ? 1 : 0);      // line of that header: newlines before it + 1
+            P.fin[2] = n_starts ? n_starts - 1 : 0;                                    // its record index
         }
     }
     // (the resident entry point caches the sniffed format per buffer: a buffer whose content changed format is caught here)

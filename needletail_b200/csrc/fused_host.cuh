@@ -54,6 +54,7 @@ struct FusedState {
     fused::TileSlot* slots = nullptr;        // ring of 1 << SLOT_SHIFT tile slots + look-back words (never cleared: generations)
     unsigned long long* cw = nullptr;
     fused::SState* final_state = nullptr;
+    unsigned long long* fa_totals = nullptr;  // FASTA: record starts / newlines of the pass in flight
     LaunchCtl* ctl = nullptr;                // NCTL blocks, device
     LaunchCtl* h_ctl = nullptr;              // NCTL blocks, pinned
     cudaEvent_t ev_done[NCTL] = {};
@@ -185,6 +186,7 @@ static int fused_init(ntg_ctx* ctx) {
     NTG_CUDA(ctx, cudaMalloc((void**)&st->ctl, NCTL * sizeof(LaunchCtl)));
     NTG_CUDA(ctx, cudaMallocHost((void**)&st->h_ctl, NCTL * sizeof(LaunchCtl)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->final_state, sizeof(fused::SState)));
+    NTG_CUDA(ctx, cudaMalloc((void**)&st->fa_totals, 2 * sizeof(unsigned long long)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->slots, (size_t(1) << SLOT_SHIFT) * sizeof(fused::TileSlot)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->cw, (size_t(1) << SLOT_SHIFT) * sizeof(unsigned long long)));
     NTG_CUDA(ctx, cudaMalloc((void**)&st->reduce_buf, 16 * sizeof(unsigned long long)));
@@ -214,7 +216,7 @@ static int fused_init(ntg_ctx* ctx) {
 static void fused_destroy(ntg_ctx* ctx) {
     FusedState* st = ctx->fused;
     if (!st) return;
-    cudaFree(st->slots); cudaFree(st->cw); cudaFree(st->ctl); cudaFree(st->final_state); cudaFreeHost(st->h_ctl);
+    cudaFree(st->slots); cudaFree(st->cw); cudaFree(st->ctl); cudaFree(st->final_state); cudaFree(st->fa_totals); cudaFreeHost(st->h_ctl);
     cudaFree(st->reduce_buf); cudaFreeHost(st->h_reduce);
     cudaFree(st->fq_info); cudaFree(st->fq_fix_list); cudaFree(st->fq_fix_phase); cudaFree(st->fq_words); cudaFree(st->fq_counters);
     for (auto& p : st->seg) cudaFree(p);
@@ -277,6 +279,8 @@ static int fused_begin_pass(ntg_ctx* ctx, int format, const ntg_tally_config* cf
     fused::Params& P = st->P;
     P = fused::Params{};
     P.slots = st->slots; P.cw = st->cw; P.slot_mask = (1u << SLOT_SHIFT) - 1; P.slot_shift = SLOT_SHIFT; P.final_state = st->final_state;
+    P.fa_totals = st->fa_totals;
+    NTG_CUDA(ctx, cudaMemsetAsync(st->fa_totals, 0, 2 * sizeof(unsigned long long), ctx->stream));
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->m ? cfg->k - cfg->m + 1 : 1; P.format = format; P.has_query = cfg->has_query ? 1 : 0; P.one = 1; P.tile_bytes = tile_bytes;
     P.qmask = format == NTG_FMT_FASTQ ? (cfg->qmask_score & 0xFFu) : 0u;
     P.spec = (allow_spec && format == NTG_FMT_FASTQ && !(cfg->flags & NTG_TALLY_NO_SPECULATION)) ? 1 : 0;

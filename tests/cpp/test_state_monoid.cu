@@ -57,6 +57,14 @@ int main() {
         if (!eq(l, all)) { std::printf("fold != direct for cuts %zu,%zu of %zu: count %llu vs %llu hdr %llx vs %llx\n", c1, c2, n,
                                        (unsigned long long)l.count, (unsigned long long)all.count, (unsigned long long)l.hdr, (unsigned long long)all.hdr); fails++; }
         if (!eq(combine(identity_state(), B), B) || !eq(combine(B, identity_state()), B)) { std::printf("identity law fails\n"); fails++; }
+        // the one-word FASTA look-back folds (kind, position) pairs: same header state as the full combine, in every grouping
+        {
+            using fused::FaState; using fused::fa_combine; using fused::fa_of;
+            const FaState fl = fa_combine(fa_combine(fa_of(A), fa_of(B)), fa_of(Cc)), fr = fa_combine(fa_of(A), fa_combine(fa_of(B), fa_of(Cc)));
+            const FaState want = fa_of(all);
+            auto same = [](const FaState& x, const FaState& y) { return x.kind == y.kind && (x.kind == 0 || x.kind == 3 || x.pos == y.pos); };
+            if (!same(fl, want) || !same(fr, want)) { std::printf("fa_combine != combine for cuts %zu,%zu of %zu: kind %u/%u/%u\n", c1, c2, n, fl.kind, fr.kind, want.kind); fails++; }
+        }
     }
     if (fails) return 1;
     std::puts("state monoid ok");
