@@ -204,11 +204,17 @@ struct __align__(16) Smem {
     volatile uint32_t pend_valid;
     uint32_t tile_idx_next;            // ticket of this CTA's next tile, claimed by walker thread 0 at the end of its walk
     uint32_t n_long;
+    uint32_t arrived;                  // warps that have finished this tile's walk (the last one takes the CTA's next ticket)
     uint32_t long_line[LONGMAX];       // line indices of long sequence lines
     uint32_t long_pref[LONGMAX + 1];   // exclusive prefix of piece counts
     int32_t bcast[4];
 };
 
+// end of a tile's walk: the last warp of the CTA to get here takes the CTA's next ticket (read by all after the next barrier)
+__device__ __forceinline__ void claim_when_last(Smem& S, uint32_t* ticket, uint32_t lane) {
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&S.arrived, 1u) == NT / 32 - 1) { S.arrived = 0; S.tile_idx_next = atomicAdd(ticket, 1u); }
+}
 // barrier of the threads that run the tile loop (all of the CTA, or the walkers only when the coordinator is decoupled)
 __device__ __forceinline__ void tile_sync() { __syncthreads(); }
 // Block-wide scans with ONE barrier (round 2: the serial fold by thread 0 between two more barriers held 4.7 % of the stall
@@ -777,7 +783,7 @@ __device__ __forceinline__ unsigned long long fa_word(uint32_t gen, uint32_t sta
 }
 // header state in front of tile t (t > 0) as an SState whose hdr field is NONE / INHDR / the stream position of the newest
 // header-ending newline (a position farther back than FA_FAR bytes comes back as "FA_FAR before the tile": beyond any halo)
-__device__ __forceinline__ SState fasta_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane) {
+__device__ __forceinline__ SState fasta_lookback(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, uint32_t* dbg = nullptr) {
     const int64_t TB = (int64_t)P.tile_bytes;
     FaState suffix{0u, 0};
     int64_t base = (int64_t)t - 1;
@@ -807,7 +813,8 @@ __device__ __forceinline__ SState fasta_lookback(const Params& P, uint64_t t, ui
         const uint32_t inc_mask = __ballot_sync(0xffffffffu, lane_state == 1), blk_mask = __ballot_sync(0xffffffffu, lane_state == 2);
         const int first_inc = inc_mask ? __ffs((int)inc_mask) - 1 : 32;
         const uint32_t need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
-        if (blk_mask & need) { __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
+        if (blk_mask & need) { if (dbg) dbg[0]++; __nanosleep(backoff); backoff = backoff < 256 ? backoff * 2 : 256; continue; }
+        if (dbg) dbg[1]++;
         const int top = first_inc < 32 ? first_inc : 31;
         FaState acc = (int)lane <= top ? mine : FaState{0u, 0};      // lanes above `top` contribute the identity
         // ordered tree reduction: lane l holds the tiles base-4l ..; higher lanes are EARLIER tiles
@@ -896,10 +903,10 @@ __device__ __forceinline__ void collect_last(const Params& P, uint64_t t_excl, u
 // Exclusive prefix of tile t in the form the line events need, by one whole warp (result in every lane).  FASTQ: `count` holds
 // enc(newlines before t) - its low two bits are the line phase - and last[] the last four newline positions; FASTA: the
 // general state.
-__device__ __forceinline__ SState tile_prefix(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, bool fasta, uint32_t& slow) {
+__device__ __forceinline__ SState tile_prefix(const Params& P, uint64_t t, uint32_t epoch, uint32_t lane, bool fasta, uint32_t& slow, uint32_t* dbg = nullptr) {
     SState pre = identity_state();
     if (t == 0) return pre;
-    if (fasta) return fasta_lookback(P, t, epoch, lane);
+    if (fasta) return fasta_lookback(P, t, epoch, lane, dbg);
     pre.count = fastq_lookback(P, t, epoch, lane);
     if (lane == 0) collect_last(P, t, pre.last, 0, slow);
 #pragma unroll
@@ -1141,13 +1148,14 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
         S.comb[i] = ri | c;
     }
     if (tid == 0) {
-        mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0;
+        mbar_init(&S.bar, 1); fence_mbar_init(); S.pend_valid = 0; S.arrived = 0;
     }
     __syncthreads();
     uint32_t parity = 0, slow = 0, my_seq = 0, mode = 0;
 #if NTG_STATS
     const long long st_t0 = clock64();
     long long st_lb = 0, st_wait = 0, st_walk = 0, st_mark = 0; uint32_t st_nlb = 0;
+    uint32_t st_dbg[2] = {0, 0}; long long st_d = 0;            // NTG_STATS == 3: look-back polls / steps, claim -> aggregate cycles
     long long st_p0 = 0, st_p1 = 0, st_p2 = 0, st_ph = 0;      // NTG_STATS == 2: thread 0's cycles in P0 / P1 / P2 (replace the look-back counters)
 #endif
     Acc acc;
@@ -1176,6 +1184,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
         if (tid == 0) S.n_long = 0;
 #if NTG_STATS
         st_ph = clock64();
+        const long long st_ph0 = st_ph;
 #endif
         // ---- P0: stage the tile (+ back halo) with one bulk async copy
         if (tid == 0 && halo + bulk) {
@@ -1294,6 +1303,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
             __syncwarp();
 #if NTG_STATS
             st_mark = clock64();
+            st_d += st_mark - st_ph0;
 #endif
             const bool had_pending = S.pend_valid != 0;
             __syncwarp();                                       // (every lane has read the flag before lane 0 sets it again below)
@@ -1311,7 +1321,11 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
                     S.pend_valid = 1;
                 }
             } else {
+#if NTG_STATS == 3
+                pre = tile_prefix(P, t, epoch, lane, fasta, slow, st_dbg);
+#else
                 pre = tile_prefix(P, t, epoch, lane, fasta, slow);
+#endif
                 if (lane == 0) {
                     publish_inclusive(P, t, epoch, pre, agg, fasta);
                     S.prefix = pre;
@@ -1326,6 +1340,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
         }
         bool have_pre = is_coord && !defer;
         if (!spec) { tile_sync(); pre = S.prefix; have_pre = true; }      // everyone needs the prefix before going on
+#if NTG_STATS == 2
+        if (fasta) { const long long c = clock64(); st_wait += c - st_ph; st_ph = c; }     // P2b + look-back wait (FASTA: every thread waits)
+#endif
         // previous newline (global position, NONE if none) `back` newlines before newline i of this tile (back >= 1)
         auto prev_nl = [&](uint32_t i, uint32_t back) -> uint64_t {
             if (i >= back) return tile_start + S.nl[i - back];
@@ -1463,17 +1480,29 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
         const long long st_done = clock64();
 #endif
 #if !NTG_EARLY_TICKET
-        if (tid == 0) S.tile_idx_next = atomicAdd(ticket, 1u);      // the next tile of this CTA (read after the barrier)
+        // The next tile of this CTA (read after a barrier).  A ticket obliges its holder to publish that tile's aggregate soon:
+        // every later tile's look-back waits for it.  So the ticket is taken by the LAST warp to finish the walk: the warps of a
+        // CTA finish far apart (the schedulers favour the oldest warp), and thread 0 taking it after its own items made the
+        // successors of the next tile poll through most of this tile's walk (NTG_STATS == 3 on the 10 kbp FASTA shape: 12 000
+        // cycles from loop top to aggregate, yet 70 000 of 153 000 cycles per tile spent polling for predecessors' aggregates).
+        // A tile made of long lines does its walking in the piece loop below and takes the ticket after that loop.
+        const bool late_claim = (uint64_t)avail > (uint64_t)(Cs + 1) * SEG;      // mean line longer than a piece: some line is long
+        // (speculative FASTQ defers its look-backs by a tile, which hides that wait: thread 0 takes the ticket — 1 % faster there)
+        if (spec) { if (tid == 0 && !late_claim) S.tile_idx_next = atomicAdd(ticket, 1u); }
+        else if (!late_claim) claim_when_last(S, ticket, lane);
+#else
+        const bool late_claim = false;
 #endif
         tile_sync();
-        next_ticket = S.tile_idx_next;
 #if NTG_STATS
         if (!fasta && !is_coord) { st_walk += st_done - st_mark; st_wait += clock64() - st_done; }
 #endif
         // ---- long lines: SEG-byte pieces shared by the whole CTA
         const uint32_t n_long = min(S.n_long, (uint32_t)LONGMAX);
         // piece length: about one piece per thread when the tile is made of long lines (at least 128 B, at most SEG)
-        const int PSEG = max(128, min(SEG, (int)(((avail + NWK - 1) / NWK + 15) & ~15u)));
+        // (every long line ends with a partial piece: leave one thread per line for it, or a few threads walk a second round)
+        const uint32_t pthreads = n_long < NWK / 2 ? NWK - n_long : NWK / 2;
+        const int PSEG = max(128, min(SEG, (int)(((avail + pthreads - 1) / pthreads + 15) & ~15u)));
         if (n_long) {
             if (tid == 0) {
                 // (order of long_line[] is arbitrary: atomics) -> prefix of piece counts
@@ -1496,8 +1525,18 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
                 if (!fasta) fastq_bound(i, la, lo, lo_exact); else fasta_bound(i, la, lo, lo_exact);
                 run_item<KW, MINI, W, FK, FM>(sb, S.lut, S.rins, S.comb, a, b, lo, lo_exact, P, acc, fasta, slow, mode);
             }
-            tile_sync();                               // (no long lines: nothing read the tile since the barrier above, and
-        }                                                  //  the reset of S.n_long at the next tile stores the value it holds)
+        }
+        if (n_long || late_claim) {                        // (no long lines: nothing read the tile since the barrier above, and
+#if !NTG_EARLY_TICKET
+            if (spec) { if (tid == 0 && late_claim) S.tile_idx_next = atomicAdd(ticket, 1u); }
+            else if (late_claim) claim_when_last(S, ticket, lane);
+#endif
+            tile_sync();                                   //  the reset of S.n_long at the next tile stores the value it holds)
+        }
+        next_ticket = S.tile_idx_next;
+#if NTG_STATS == 2
+        if (fasta) st_walk += clock64() - st_ph;            // region scan + short lines + long-line pieces
+#endif
         my_seq++;
     }
 
@@ -1508,7 +1547,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_fused(const Params P, const
         const unsigned long long life = (unsigned long long)(clock64() - st_t0);
         if (tid == 0) { atomicAdd(&P.tallies[9], life); atomicMax(&P.tallies[12], life);
                         atomicAdd(&P.tallies[14], (unsigned long long)st_wait); atomicAdd(&P.tallies[15], (unsigned long long)st_walk); }
-#if NTG_STATS == 2
+#if NTG_STATS == 3
+        if (tid == NTW) { atomicAdd(&P.tallies[10], (unsigned long long)st_lb); atomicAdd(&P.tallies[11], (unsigned long long)st_nlb);
+                          atomicAdd(&P.tallies[14], (unsigned long long)st_d); atomicAdd(&P.tallies[15], (unsigned long long)st_dbg[0]); atomicAdd(&P.tallies[6], (unsigned long long)st_dbg[1]); }
+#elif NTG_STATS == 2
         if (tid == 0) { atomicAdd(&P.tallies[10], (unsigned long long)st_p0); atomicAdd(&P.tallies[11], (unsigned long long)st_p1); atomicAdd(&P.tallies[6], (unsigned long long)st_p2); }   // ([6] = n_query: unused without a query)
 #else
         if (tid == NTW) { atomicAdd(&P.tallies[10], (unsigned long long)st_lb); atomicAdd(&P.tallies[11], (unsigned long long)st_nlb); }

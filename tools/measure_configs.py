@@ -46,6 +46,7 @@ def wrapped_fasta(reads, L, width, seed):
 
 def main():
     ctx = nt.Context(0)
+    ctx.tally_flags = int(os.environ.get("NT_MC_FLAGS", "0"))     # 4 = NTG_TALLY_NO_FASTPATH: the tile kernel on short-read FASTQ too
     out = []
     only = os.environ.get("NT_MC_ONLY")
     configs = [CONFIGS[int(i)] for i in only.split(",")] if only else CONFIGS
