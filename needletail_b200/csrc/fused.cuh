@@ -807,7 +807,9 @@ __device__ __forceinline__ SState fasta_lookback(const Params& P, uint64_t t, ui
             }
             if (lane_state == 0) {
                 if (st == 0) lane_state = 2;
-                else { mine = fa_combine(FaState{kind, pos}, mine); if (st == 2) lane_state = 1; }
+                // (an aggregate with a header event of its own absorbs everything before it — fa_combine(a, b) = b for
+                //  b.kind >= 2 — so it ends the look-back like an inclusive prefix does: no wait for farther predecessors)
+                else { mine = fa_combine(FaState{kind, pos}, mine); if (st == 2 || kind >= 2u) lane_state = 1; }
             }
         }
         const uint32_t inc_mask = __ballot_sync(0xffffffffu, lane_state == 1), blk_mask = __ballot_sync(0xffffffffu, lane_state == 2);
