@@ -9,7 +9,7 @@ plus batch forms of the ``Sequence`` trait methods
 anywhere, but every call needs a B200 (``Context()`` raises ``NtgError`` otherwise).
 """
 import ctypes as C
-import os
+import os, time
 import zlib
 
 import numpy as np
@@ -301,16 +301,17 @@ class Context:
             at_eof = pos + ln == n
             out = C.POINTER(_Records)(); consumed = C.c_uint64()
             win = arr[pos:pos + ln]
+            t0 = time.perf_counter()
             self._ck(self.lib.ntg_parse_fastx_chunk(self.h, _ptr(win), ln, fmt, int(at_eof), C.byref(out), C.byref(consumed)))
+            self.parse_seconds += time.perf_counter() - t0          # time inside the C ABI (this generator adds table copies)
             try:
                 p = Parsed(win, out.contents, with_records)
             finally:
                 self.lib.ntg_records_free(out)
             fmt = {"fasta": 1, "fastq": 2}.get(p.format, 0)
-            if len(p.table):
-                p.table[:, [0, 1, 2, 3, 4, 7]] += np.uint64(pos)
-                if p.format == "fastq":
-                    p.table[:, [5, 6]] += np.uint64(pos)
+            if len(p.table) and (pos or line_base):
+                for c in (0, 1, 2, 3, 4, 7) + ((5, 6) if p.format == "fastq" else ()):
+                    p.table[:, c] += np.uint64(pos)
                 p.table[:, 9] += np.uint64(line_base)
                 for r in p.records:
                     r.byte += pos; r.line += line_base
@@ -408,6 +409,7 @@ class Context:
         return out
 
     # ---- (3) fused hot path
+    parse_seconds = 0.0      # seconds spent inside ntg_parse_fastx_chunk (parse_chunks)
     tally_flags = 0          # NTG_TALLY_* bits sent with every tally call (1 = no FASTQ line-phase speculation; diagnostic)
 
     def _cfg(self, k, m, iupac, query, qmask=0):

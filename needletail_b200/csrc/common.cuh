@@ -5,12 +5,66 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/ntgpu.h"
 
 // ----------------------------------------------------------------------------- context
+// Grow-only device scratch of the materialising paths (record scanner): a context keeps its buffers between calls instead
+// of paying cudaMalloc / cudaFree (which synchronise the device) for ~6 buffers per window.  Calls on one context are serial.
+struct ScratchPool {
+    enum Slot { BYTES, COUNTS, NLPOS, STPOS, STORD, STCR, RECS, ERRKIND, MISC, SLOTS };
+    void* dev[SLOTS] = {};
+    size_t cap[SLOTS] = {};
+    void* get(int slot, size_t bytes) {                  // nullptr: out of device memory
+        if (dev[slot] && bytes <= cap[slot]) return dev[slot];
+        if (dev[slot]) { cudaFree(dev[slot]); dev[slot] = nullptr; cap[slot] = 0; }
+        size_t want = bytes + bytes / 8 + 256;            // headroom: windows of a stream differ a little in their counts
+        if (cudaMalloc(&dev[slot], want) != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes ? bytes : 1;
+            if (cudaMalloc(&dev[slot], want) != cudaSuccess) { cudaGetLastError(); dev[slot] = nullptr; return nullptr; }
+        }
+        cap[slot] = want;
+        return dev[slot];
+    }
+    void release() { for (int i = 0; i < SLOTS; i++) { if (dev[i]) cudaFree(dev[i]); dev[i] = nullptr; cap[i] = 0; } }
+};
+// Pinned host buffers of record tables: a freed ntg_records hands its buffer back (pinning costs ~0.1 ms per MiB).  Shared by the
+// context and the tables it returned, so a table may outlive its context.
+struct PinPool {
+    struct Ent { void* p; size_t cap; };
+    std::mutex mu;
+    bool closed = false;
+    std::vector<Ent> spare;
+    void* take(size_t bytes, size_t* cap_out) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < spare.size(); i++)
+                if (spare[i].cap >= bytes) { Ent e = spare[i]; spare.erase(spare.begin() + i); *cap_out = e.cap; return e.p; }
+            if (!spare.empty()) { cudaFreeHost(spare.back().p); spare.pop_back(); }      // too small: replace it
+        }
+        void* p = nullptr;
+        const size_t want = bytes + bytes / 8 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *cap_out = want;
+        return p;
+    }
+    void give(void* p, size_t cap) {
+        std::lock_guard<std::mutex> g(mu);
+        if (closed || spare.size() >= 2) cudaFreeHost(p); else spare.push_back(Ent{p, cap});
+    }
+    void close() {
+        std::lock_guard<std::mutex> g(mu);
+        closed = true;
+        for (auto& e : spare) cudaFreeHost(e.p);
+        spare.clear();
+    }
+};
+
 struct ntg_ctx {
     int device = 0;
     int sm_count = 0;
@@ -25,6 +79,8 @@ struct ntg_ctx {
     void* nccl_comm = nullptr;
     int nccl_ranks = 1, nccl_rank = 0;
     void* nccl_buf = nullptr;             // device staging for the tallies all-reduce
+    ScratchPool scratch;
+    std::shared_ptr<PinPool> pinpool = std::make_shared<PinPool>();
 };
 
 int ntg_set_error(ntg_ctx* ctx, int status, const char* fmt, ...);

@@ -95,6 +95,8 @@ void ntg_destroy(ntg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ntg_comm_destroy(ctx);
     fused_destroy(ctx);
+    ctx->scratch.release();
+    ctx->pinpool->close();
     for (auto& e : ctx->events) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -1,10 +1,15 @@
 // parse.cuh — FASTX record scanner producing the record table (materialising path).
 //
-// Whole-buffer formulation of the reference's readers: delimiter flags ->
-// device-wide scans (newline ordinal per byte) -> compaction of newline / record-start
-// positions -> one thread per record fills the ntg_record row and validates it.
+// Whole-buffer formulation of the reference's readers in two passes over the window:
+//   k_index_count : per 8 KiB tile, the number of newlines (FASTA also: record starts — '>' at a line start — and '\r')
+//   k_index_scan  : exclusive scan of the tile counts (one CTA)
+//   k_index_emit  : the ordered lists — position of every newline; FASTA: position, newline ordinal and '\r' ordinal of every
+//                   record start (what num_bases needs: fasta.rs:102-107 without a per-byte index)
+// then one thread per record fills the ntg_record row and validates it.
 //   FASTQ: record r owns newlines 4r..4r+3          (src/parser/fastq.rs:155-187)
 //   FASTA: a record starts at byte 0 and after every "\n>"   (src/parser/fasta.rs:220-243)
+// Round 1 wrote a flag byte and a 32-bit ordinal per input byte (12 bytes of traffic and 9 bytes of scratch per byte, allocated
+// per call); this form reads the window twice and writes 4 bytes per newline, from buffers the context keeps (ScratchPool).
 // Only the O(1) end-of-stream rules (fastq.rs:337-356, fasta.rs:200-216) run on the host, on the
 // few newline positions the device hands back.  Part of the unity build (ntgpu.cu).
 #pragma once
@@ -15,21 +20,127 @@ namespace parse {
 constexpr int BLOCK = 256;
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
 
-__global__ void __launch_bounds__(BLOCK) k_flags(const uint8_t* __restrict__ bytes, uint32_t n, int fasta,
-                                                 uint8_t* __restrict__ f_nl, uint8_t* __restrict__ f_cr, uint8_t* __restrict__ f_st) {
-    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
-    if (g >= n) return;
-    uint8_t b = bytes[g];
-    f_nl[g] = b == '\n';
-    if (fasta) {
-        f_cr[g] = b == '\r';
-        f_st[g] = (b == '>') && (g == 0 || bytes[g - 1] == '\n');
+constexpr int IDX_PER = 32;                       // bytes per thread: one bit mask per delimiter
+constexpr int IDX_TILE = BLOCK * IDX_PER;         // 8 KiB per CTA
+struct Masks { uint32_t nl, cr, gt; };           // bit i = byte i of the thread's span
+
+// 4-bit mask of the bytes of w equal to the byte replicated in pat (exact: no false positives from borrows)
+__device__ __forceinline__ uint32_t eq4(uint32_t w, uint32_t pat) {
+    const uint32_t x = w ^ pat;
+    const uint32_t t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);      // 0x80 in the bytes that are zero
+    return (((t >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+__device__ __forceinline__ Masks span_masks(const uint8_t* __restrict__ bytes, uint32_t g0, uint32_t n, bool fasta, bool aligned) {
+    Masks m{0, 0, 0};
+    if (g0 >= n) return m;
+    uint32_t w[8];
+    if (aligned && g0 + IDX_PER <= n) {
+        const uint4 a = *reinterpret_cast<const uint4*>(bytes + g0), b = *reinterpret_cast<const uint4*>(bytes + g0 + 16);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const uint32_t g = g0 + 4 * q + j; if (g < n) v |= (uint32_t)bytes[g] << (8 * j); }
+            w[q] = v;                                 // (bytes behind the window read as 0: no delimiter)
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        m.nl |= eq4(w[q], 0x0A0A0A0Au) << (4 * q);
+        if (fasta) { m.cr |= eq4(w[q], 0x0D0D0D0Du) << (4 * q); m.gt |= eq4(w[q], 0x3E3E3E3Eu) << (4 * q); }
+    }
+    return m;
+}
+// FASTA record starts of the span: '>' at byte 0 of the window or right behind a newline (fasta.rs:220-243)
+__device__ __forceinline__ uint32_t start_mask(const uint8_t* __restrict__ bytes, uint32_t g0, uint32_t n, const Masks& m) {
+    if (g0 >= n || !m.gt) return 0;
+    const uint32_t prev_nl = (g0 == 0 || bytes[g0 - 1] == '\n') ? 1u : 0u;
+    return m.gt & ((m.nl << 1) | prev_nl);
+}
+// per tile: counts of newlines / record starts / '\r'
+__global__ void __launch_bounds__(BLOCK) k_index_count(const uint8_t* __restrict__ bytes, uint32_t n, int fasta, int aligned,
+                                                       uint32_t* __restrict__ cnt_nl, uint32_t* __restrict__ cnt_st, uint32_t* __restrict__ cnt_cr) {
+    __shared__ uint32_t red[BLOCK / 32][3];
+    const uint32_t g0 = blockIdx.x * IDX_TILE + threadIdx.x * IDX_PER;
+    const Masks m = span_masks(bytes, g0, n, fasta != 0, aligned != 0);
+    uint32_t c0 = __popc(m.nl), c1 = fasta ? __popc(start_mask(bytes, g0, n, m)) : 0u, c2 = __popc(m.cr);
+    c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = c0; red[threadIdx.x >> 5][1] = c1; red[threadIdx.x >> 5][2] = c2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        uint32_t s = 0;
+        for (int wi = 0; wi < BLOCK / 32; wi++) s += red[wi][threadIdx.x];
+        (threadIdx.x == 0 ? cnt_nl : threadIdx.x == 1 ? cnt_st : cnt_cr)[blockIdx.x] = s;
     }
 }
-__global__ void __launch_bounds__(BLOCK) k_compact(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ idx, uint32_t n,
-                                                   uint32_t* __restrict__ outpos) {
-    uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
-    if (g < n && flags[g]) outpos[idx[g]] = g;
+// in-place exclusive scan of the three count arrays (n_tiles entries each), totals at [n_tiles]; one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_index_scan(uint32_t* __restrict__ a0, uint32_t* __restrict__ a1, uint32_t* __restrict__ a2, uint32_t n_tiles, int n_arrays) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    for (int q = 0; q < n_arrays; q++) {
+        uint32_t* a = q == 0 ? a0 : q == 1 ? a1 : a2;
+        if (threadIdx.x == 0) carry_s = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < n_tiles; base += 1024) {
+            const uint32_t i = base + threadIdx.x;
+            const uint32_t v = i < n_tiles ? a[i] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= d) incl += t; }
+            if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t ws = wsum[threadIdx.x];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += t; }
+                wsum[threadIdx.x] = ws;                   // inclusive warp totals
+            }
+            __syncthreads();
+            const uint32_t carry = carry_s;
+            const uint32_t before = carry + ((threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0u) + incl - v;
+            if (i < n_tiles) a[i] = before;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry_s = before + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) a[n_tiles] = carry_s;
+        __syncthreads();
+    }
+}
+// ordered lists: nlpos[] (every newline); FASTA: stpos[] / stord[] / stcr[] (record start, newlines before it, '\r' before it)
+__global__ void __launch_bounds__(BLOCK) k_index_emit(const uint8_t* __restrict__ bytes, uint32_t n, int fasta, int aligned,
+                                                      const uint32_t* __restrict__ pre_nl, const uint32_t* __restrict__ pre_st, const uint32_t* __restrict__ pre_cr,
+                                                      uint32_t* __restrict__ nlpos, uint32_t* __restrict__ stpos, uint32_t* __restrict__ stord,
+                                                      uint32_t* __restrict__ stcr) {
+    __shared__ unsigned long long wsum[BLOCK / 32];
+    const uint32_t g0 = blockIdx.x * IDX_TILE + threadIdx.x * IDX_PER;
+    const Masks m = span_masks(bytes, g0, n, fasta != 0, aligned != 0);
+    const uint32_t st = fasta ? start_mask(bytes, g0, n, m) : 0u;
+    // one block scan of the three per-thread counts (<= 32 each, <= 8192 per tile: 14 bits per field)
+    const unsigned long long v = (unsigned long long)__popc(m.nl) | ((unsigned long long)__popc(st) << 14) | ((unsigned long long)__popc(m.cr) << 28);
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= d) incl += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long before = incl - v;
+    for (int wi = 0; wi < (int)(threadIdx.x >> 5); wi++) before += wsum[wi];
+    uint32_t o_nl = pre_nl[blockIdx.x] + (uint32_t)(before & 0x3FFFu);
+    uint32_t mk = m.nl;
+    while (mk) { const int b = __ffs((int)mk) - 1; mk &= mk - 1; nlpos[o_nl++] = g0 + b; }
+    if (st) {
+        const uint32_t nl0 = pre_nl[blockIdx.x] + (uint32_t)(before & 0x3FFFu), cr0 = pre_cr[blockIdx.x] + (uint32_t)((before >> 28) & 0x3FFFu);
+        uint32_t o_st = pre_st[blockIdx.x] + (uint32_t)((before >> 14) & 0x3FFFu);
+        mk = st;
+        while (mk) {
+            const int b = __ffs((int)mk) - 1; mk &= mk - 1;
+            const uint32_t below = (1u << b) - 1u;
+            stpos[o_st] = g0 + b; stord[o_st] = nl0 + __popc(m.nl & below); stcr[o_st] = cr0 + __popc(m.cr & below);
+            o_st++;
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t trim_cr_end(const uint8_t* __restrict__ bytes, uint32_t b, uint32_t e) {
@@ -61,18 +172,18 @@ __global__ void __launch_bounds__(BLOCK) k_fastq_records(const uint8_t* __restri
     if (ek) atomicMin(first_err, r);
 }
 
-// one thread per FASTA record start (fasta.rs:16-108,190-195)
+// one thread per FASTA record start (fasta.rs:16-108,190-195).  stord / stcr: newlines / '\r' bytes in front of each start.
 __global__ void __launch_bounds__(BLOCK) k_fasta_records(const uint8_t* __restrict__ bytes, uint32_t n,
-                                                         const uint32_t* __restrict__ stpos, uint32_t n_starts,
-                                                         const uint32_t* __restrict__ nlidx, const uint32_t* __restrict__ cridx,
-                                                         const uint32_t* __restrict__ nlpos, uint32_t n_nl,
+                                                         const uint32_t* __restrict__ stpos, const uint32_t* __restrict__ stord,
+                                                         const uint32_t* __restrict__ stcr, uint32_t n_starts,
+                                                         const uint32_t* __restrict__ nlpos, uint32_t n_nl, uint32_t n_cr,
                                                          ntg_record* __restrict__ recs, uint32_t* __restrict__ last_bad,
                                                          uint32_t* __restrict__ first_le) {
     uint32_t r = blockIdx.x * BLOCK + threadIdx.x;
     if (r >= n_starts) return;
     uint32_t start = stpos[r];
     bool is_last = (r + 1 == n_starts);
-    uint32_t ord = nlidx[start];                              // newlines before `start` (none at start: it is '>')
+    uint32_t ord = stord[r];                                  // newlines before `start` (none at start: it is '>')
     uint32_t first_nl = ord < n_nl ? nlpos[ord] : 0xFFFFFFFFu;
     uint32_t last;
     if (!is_last) last = stpos[r + 1] - 1;                    // the '\n' in front of the next '>'
@@ -89,7 +200,21 @@ __global__ void __launch_bounds__(BLOCK) k_fasta_records(const uint8_t* __restri
     o.qual_b = o.qual_e = 0;
     o.all_e = last;
     uint32_t sb = (uint32_t)o.seq_b, se = (uint32_t)o.seq_e;
-    o.num_bases = (uint64_t)(se - sb) - (nlidx[se] - nlidx[sb]) - (cridx[se] - cridx[sb]);   // fasta.rs:102-107
+    // num_bases = bytes of [sb, se) that are neither '\n' nor '\r' (fasta.rs:102-107), from the ordinals at the record starts:
+    //   newlines before sb = ord + 1 (the header's newline); before se = those before `last` (the bytes of [se, last) are a trimmed '\r')
+    //   '\r' before sb = stcr[r] + those of the header line (counted here: header lines are short); before se = those before the
+    //   next start (or all of the window) minus the trimmed one
+    uint64_t nb = 0;
+    if (se > sb) {
+        const uint32_t nl_before_last = is_last ? n_nl - ((bytes[n - 1] == '\n') ? 1u : 0u) : stord[r + 1] - 1u;
+        const uint32_t nl_in = nl_before_last - (ord + 1u);
+        uint32_t cr_hdr = 0;
+        for (uint32_t q = start; q < sb; q++) cr_hdr += bytes[q] == '\r';
+        const uint32_t cr_before_se = (is_last ? n_cr : stcr[r + 1]) - (last - se);
+        const uint32_t cr_in = cr_before_se - (stcr[r] + cr_hdr);
+        nb = (uint64_t)(se - sb) - nl_in - cr_in;
+    }
+    o.num_bases = nb;
     o.line = 1 + (uint64_t)ord;
     recs[r] = o;
     // line_ending(): taken from the first record whose all() contains a newline (fasta.rs:358-360, utils.rs:106-117)
@@ -97,7 +222,18 @@ __global__ void __launch_bounds__(BLOCK) k_fasta_records(const uint8_t* __restri
 }
 }  // namespace parse
 
-struct RecordsPriv { PinBuf<ntg_record> recs; };
+struct RecordsPriv {                       // the table's pinned buffer goes back to the context's pool when the table is freed
+    struct Recs {
+        ntg_record* p = nullptr; size_t cap = 0;
+        std::shared_ptr<PinPool> pool;
+        bool alloc(size_t rows) {               // true: failed
+            void* q = pool->take((rows ? rows : 1) * sizeof(ntg_record), &cap);
+            p = static_cast<ntg_record*>(q);
+            return q == nullptr;
+        }
+    } recs;
+    ~RecordsPriv() { if (recs.p) recs.pool->give(recs.p, recs.cap); }
+};
 
 // Host-side access to a few input bytes: straight from the caller's host copy when there is one,
 // else small device-to-host reads (device-resident inputs).
@@ -148,6 +284,7 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
     if (n >= 0xFFFFFFF0ull) return ntg_set_error(ctx, NTG_EUNSUPPORTED, "ntg_parse_fastx: feed at most 4 GiB per call");
     auto* res = new ntg_records();
     auto* priv = new RecordsPriv();
+    priv->recs.pool = ctx->pinpool;
     std::memset(res, 0, sizeof(*res));
     res->_priv = priv;
     auto done = [&](int st) { if (st != NTG_OK) { delete priv; delete res; } else *out = res; return st; };
@@ -168,45 +305,60 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
     const bool fasta = res->format == NTG_FMT_FASTA;
     const uint32_t n32 = (uint32_t)n;
 
-    DevBuf<uint8_t> dbytes_local, f_nl, f_cr, f_st;
-    DevBuf<uint8_t>& dbytes_own = keep_dbytes ? *keep_dbytes : dbytes_local;
-    DevBuf<uint32_t> nlidx, cridx, stidx, tmp, nlpos, stpos;
+    // device buffers: the context's grow-only scratch, except the copies a caller takes over (keep_dbytes / keep_drecs)
+    ScratchPool& pool = ctx->scratch;
     struct { const uint8_t* p; } dbytes{dev_in};
     if (!dev_in) {
-        if (dbytes_own.alloc(n)) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
-        dbytes.p = dbytes_own.p;
+        if (keep_dbytes) { if (keep_dbytes->alloc(n)) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed")); dbytes.p = keep_dbytes->p; }
+        else {
+            dbytes.p = (const uint8_t*)pool.get(ScratchPool::BYTES, n);
+            if (!dbytes.p) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
+        }
     }
-    if (f_nl.alloc(n) || nlidx.alloc(n + 1) || tmp.alloc(scan_tmp_count(n)))
-        return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
-    if (fasta && (f_cr.alloc(n) || f_st.alloc(n) || cridx.alloc(n + 1) || stidx.alloc(n + 1)))
-        return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
+    const uint32_t n_tiles = (uint32_t)((n + IDX_TILE - 1) / IDX_TILE);
+    uint32_t* counts = (uint32_t*)pool.get(ScratchPool::COUNTS, 3 * ((size_t)n_tiles + 1) * sizeof(uint32_t));
+    uint32_t* misc = (uint32_t*)pool.get(ScratchPool::MISC, 64);
+    if (!counts || !misc) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
+    uint32_t *cnt_nl = counts, *cnt_st = counts + (n_tiles + 1), *cnt_cr = counts + 2 * ((size_t)n_tiles + 1);
 #define PCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return done(ntg_set_error(ctx, NTG_ECUDA, "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(_e))); } while (0)
 #define PTRY(expr) do { int _s = (expr); if (_s != NTG_OK) return done(_s); } while (0)
-    if (!dev_in) PCUDA(cudaMemcpyAsync(dbytes_own.p, bytes, n, cudaMemcpyHostToDevice, ctx->stream));
-    k_flags<<<grid_for(n), BLOCK, 0, ctx->stream>>>(dbytes.p, n32, fasta ? 1 : 0, f_nl.p, f_cr.p, f_st.p);
-    ctx->launches++;
-    PTRY(exclusive_scan_u8(ctx, f_nl.p, nlidx.p, n, tmp.p));
-    uint32_t n_nl = 0, n_st = 0;
-    PCUDA(cudaMemcpyAsync(&n_nl, nlidx.p + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev_in) PCUDA(cudaMemcpyAsync(const_cast<uint8_t*>(dbytes.p), bytes, n, cudaMemcpyHostToDevice, ctx->stream));
+    const int aligned = ((uintptr_t)dbytes.p & 15) == 0;
+    k_index_count<<<n_tiles, BLOCK, 0, ctx->stream>>>(dbytes.p, n32, fasta ? 1 : 0, aligned, cnt_nl, cnt_st, cnt_cr);
+    k_index_scan<<<1, 1024, 0, ctx->stream>>>(cnt_nl, cnt_st, cnt_cr, n_tiles, fasta ? 3 : 1);
+    ctx->launches += 2;
+    uint32_t n_nl = 0, n_st = 0, n_cr = 0;
+    PCUDA(cudaMemcpyAsync(&n_nl, cnt_nl + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (fasta) {
-        PTRY(exclusive_scan_u8(ctx, f_cr.p, cridx.p, n, tmp.p));
-        PTRY(exclusive_scan_u8(ctx, f_st.p, stidx.p, n, tmp.p));
-        PCUDA(cudaMemcpyAsync(&n_st, stidx.p + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PCUDA(cudaMemcpyAsync(&n_st, cnt_st + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PCUDA(cudaMemcpyAsync(&n_cr, cnt_cr + n_tiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     PCUDA(cudaStreamSynchronize(ctx->stream));
-    if (nlpos.alloc(n_nl) || (fasta && stpos.alloc(n_st))) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
-    k_compact<<<grid_for(n), BLOCK, 0, ctx->stream>>>(f_nl.p, nlidx.p, n32, nlpos.p);
+    struct { uint32_t* p; } nlpos{nullptr}, stpos{nullptr}, stord{nullptr}, stcr{nullptr};
+    nlpos.p = (uint32_t*)pool.get(ScratchPool::NLPOS, ((size_t)n_nl + 1) * 4);
+    if (fasta) {
+        stpos.p = (uint32_t*)pool.get(ScratchPool::STPOS, ((size_t)n_st + 1) * 4);
+        stord.p = (uint32_t*)pool.get(ScratchPool::STORD, ((size_t)n_st + 1) * 4);
+        stcr.p = (uint32_t*)pool.get(ScratchPool::STCR, ((size_t)n_st + 1) * 4);
+    }
+    if (!nlpos.p || (fasta && (!stpos.p || !stord.p || !stcr.p))) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
+    k_index_emit<<<n_tiles, BLOCK, 0, ctx->stream>>>(dbytes.p, n32, fasta ? 1 : 0, aligned, cnt_nl, cnt_st, cnt_cr, nlpos.p, stpos.p, stord.p, stcr.p);
     ctx->launches++;
-    if (fasta) { k_compact<<<grid_for(n), BLOCK, 0, ctx->stream>>>(f_st.p, stidx.p, n32, stpos.p); ctx->launches++; }
 
-    DevBuf<ntg_record> drecs_own;
-    DevBuf<ntg_record>& drecs = keep_drecs ? *keep_drecs : drecs_own;
+    // record table on the device: n_recs_cap rows
+    struct { ntg_record* p; } drecs{nullptr};
+    auto alloc_recs = [&](size_t rows) -> bool {
+        if (keep_drecs) { if (keep_drecs->alloc(rows)) return false; drecs.p = keep_drecs->p; return true; }
+        drecs.p = (ntg_record*)pool.get(ScratchPool::RECS, (rows ? rows : 1) * sizeof(ntg_record));
+        return drecs.p != nullptr;
+    };
     uint32_t le_rec = 0;     // index of the first record whose all() contains a newline (FASTQ: always record 0)
     if (!fasta) {
         // -------------------------------------------------------------------------- FASTQ
         uint32_t n_complete = n_nl / 4, rem = n_nl % 4;
-        DevBuf<uint8_t> errkind; DevBuf<uint32_t> first_err;
-        if (drecs.alloc((size_t)n_complete + 1) || errkind.alloc(n_complete) || first_err.alloc(1))      // (+1: a last record without newline)
+        struct { uint8_t* p; } errkind{(uint8_t*)pool.get(ScratchPool::ERRKIND, (size_t)n_complete + 1)};
+        struct { uint32_t* p; } first_err{misc};
+        if (!alloc_recs((size_t)n_complete + 1) || !errkind.p)      // (+1: a last record without newline)
             return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
         PCUDA(cudaMemsetAsync(first_err.p, 0xFF, 4, ctx->stream));
         if (n_complete) {
@@ -273,7 +425,7 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         }
         uint64_t total = n_ok + (have_eof_rec ? 1 : 0);
         if (priv->recs.alloc(total)) return done(ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed"));
-        if (n_ok) PCUDA(cudaMemcpy(priv->recs.p, drecs.p, n_ok * sizeof(ntg_record), cudaMemcpyDeviceToHost));
+        if (n_ok) { PCUDA(cudaMemcpyAsync(priv->recs.p, drecs.p, n_ok * sizeof(ntg_record), cudaMemcpyDeviceToHost, ctx->stream)); PCUDA(cudaStreamSynchronize(ctx->stream)); }
         if (have_eof_rec) {
             priv->recs.p[n_ok] = eof_rec;
             PCUDA(cudaMemcpy(drecs.p + n_ok, &eof_rec, sizeof(eof_rec), cudaMemcpyHostToDevice));      // (callers that keep the device table)
@@ -287,11 +439,11 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         }
     } else {
         // -------------------------------------------------------------------------- FASTA
-        DevBuf<uint32_t> last_bad, first_le;
-        if (drecs.alloc(n_st) || last_bad.alloc(1) || first_le.alloc(1)) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
+        struct { uint32_t* p; } last_bad{misc + 1}, first_le{misc + 2};
+        if (!alloc_recs(n_st)) return done(ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed"));
         PCUDA(cudaMemsetAsync(last_bad.p, 0, 4, ctx->stream));
         PCUDA(cudaMemsetAsync(first_le.p, 0xFF, 4, ctx->stream));
-        k_fasta_records<<<grid_for(n_st), BLOCK, 0, ctx->stream>>>(dbytes.p, n32, stpos.p, n_st, nlidx.p, cridx.p, nlpos.p, n_nl, drecs.p, last_bad.p, first_le.p);
+        k_fasta_records<<<grid_for(n_st), BLOCK, 0, ctx->stream>>>(dbytes.p, n32, stpos.p, stord.p, stcr.p, n_st, nlpos.p, n_nl, n_cr, drecs.p, last_bad.p, first_le.p);
         ctx->launches++;
         PCUDA(cudaGetLastError());
         uint32_t bad = 0;
@@ -300,7 +452,7 @@ static int run_parse_device(ntg_ctx* ctx, const uint8_t* bytes, const uint8_t* d
         PCUDA(cudaStreamSynchronize(ctx->stream));
         uint64_t total = n_st - (bad ? 1 : 0);
         if (priv->recs.alloc(n_st)) return done(ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed"));
-        PCUDA(cudaMemcpy(priv->recs.p, drecs.p, (size_t)n_st * sizeof(ntg_record), cudaMemcpyDeviceToHost));
+        PCUDA(cudaMemcpyAsync(priv->recs.p, drecs.p, (size_t)n_st * sizeof(ntg_record), cudaMemcpyDeviceToHost, ctx->stream)); PCUDA(cudaStreamSynchronize(ctx->stream));
         res->n_records = total; res->records = priv->recs.p;
         if (!at_eof) {
             // the last record start of the window is not delivered: the record may continue behind the window

@@ -549,3 +549,56 @@ def test_quality_mask_fused_into_the_tally(ctx, fixtures):  # src/sequence.rs:28
     assert got["err_kind"] == "InvalidStart" and got["n_records"] == 900 and got["kmer_sum_lo"] == exp["kmer_sum_lo"]
     fa = fixtures["data/28S.fasta"]
     assert ctx.tally(fa, k=31, qmask=50)["kmer_sum_lo"] == ctx.tally(fa, k=31)["kmer_sum_lo"]
+
+
+def test_record_table_many_tiles(ctx):  # the delimiter index of the record scanner across 8 KiB tiles (src/parser/fasta.rs:102-107,220-243)
+    rng = random.Random(77)
+
+    def seqline(n):
+        return bytes(rng.choice(b"ACGTNacgt") for _ in range(n))
+
+    # wrapped FASTA: CRLF and LF mixed, '\r' inside headers and inside sequence lines, blank lines, '>' inside lines,
+    # records from empty to several tiles long; then the same through small windows (unaligned window starts)
+    parts = []
+    for r in range(400):
+        hdr = b">r%d desc\rwith cr" % r if r % 7 == 0 else b">r%d" % r
+        le = b"\r\n" if r % 3 == 0 else b"\n"
+        parts.append(hdr + le)
+        total = rng.choice((0, 1, 59, 60, 61, 500, 9000, 30000))
+        while total > 0:
+            w = min(total, rng.choice((60, 70, 1, 8192)))
+            line = bytearray(seqline(w))
+            if rng.random() < 0.05:
+                line[rng.randrange(len(line))] = ord("\r")
+            if rng.random() < 0.05:
+                line[rng.randrange(len(line))] = ord(">")
+            parts.append(bytes(line) + le)
+            total -= w
+        if r % 11 == 0:
+            parts.append(le)
+    fa = b"".join(parts)
+    assert len(fa) > 40 * 8192
+    assert_parse(ctx, fa, "wrapped fasta")
+    assert_parse(ctx, fa[:-1], "wrapped fasta, no final newline")
+    assert_parse(ctx, fa + b">last", "wrapped fasta, header only at the end")
+    exp = O.parse_fastx(fa)
+    for window in (100_003, 1 << 20):
+        rows = np.concatenate([p.table for p in ctx.parse_chunks(fa, window, with_records=False)])
+        et = exp.table[:, :10].copy()
+        empty = et[:, 3] == et[:, 4]
+        et[empty, 3] = et[empty, 4] = rows[empty, 3] = rows[empty, 4] = 0
+        assert np.array_equal(rows, et), window
+    # FASTQ across tiles: CRLF, long reads, a quality line starting with '@'
+    recs = []
+    for r in range(3000):
+        L = rng.choice((1, 100, 151, 5000))
+        le = b"\r\n" if r % 2 else b"\n"
+        q = bytearray(rng.choice(b"@+IJ#") for _ in range(L))
+        recs.append(b"@q%d" % r + le + seqline(L) + le + b"+" + le + bytes(q) + le)
+    fq = b"".join(recs)
+    assert_parse(ctx, fq, "fastq tiles")
+    assert_parse(ctx, fq[:-2], "fastq tiles, no final newline")
+    assert_parse(ctx, fq[: len(fq) // 2], "fastq tiles, truncated")
+    exp = O.parse_fastx(fq)
+    rows = np.concatenate([p.table for p in ctx.parse_chunks(fq, 70_001, with_records=False)])
+    assert np.array_equal(rows, exp.table[:, :10])

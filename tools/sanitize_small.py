@@ -22,6 +22,14 @@ for name, data, k, m in cases:
     assert all(got[x] == exp[x] for x in KEYS), (name, got, exp)
     s = ctx.stream(k=k, m=m); s.feed(data[:100000]); s.feed(data[100000:]); got = s.finish()
     assert all(got[x] == exp[x] for x in KEYS), (name, "stream")
+# record scanner (delimiter index + one thread per record), whole buffer and windows
+for name, data in (("fastq", fq), ("fasta", fa), ("fasta crlf", fa.replace(b"\n", b"\r\n")), ("fastq cut", fq[:-100])):
+    exp = O.parse_fastx(data)
+    got = ctx.parse(data)
+    assert got.err_kind == exp.err_kind and len(got.records) == len(exp.records), name
+    assert (got.table[:, 8] == exp.table[:, 8]).all() and (got.table[:, 7] == exp.table[:, 7]).all(), name
+    rows = sum(len(p.table) for p in ctx.parse_chunks(data, 50_001, with_records=False))
+    assert rows == len(exp.records), name
 ctx.tally_flags = 1                                                     # NTG_TALLY_NO_SPECULATION
 got = ctx.tally(fq, k=31, m=21); exp = O.tally_fastx(fq, k=31, m=21)
 assert all(got[x] == exp[x] for x in KEYS)
