@@ -23,6 +23,7 @@
 // runs longer than the halo) raises a flag and the host re-runs the exact materialising path.
 // Part of the unity build (ntgpu.cu).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace fused {
@@ -557,9 +558,20 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     constexpr uint32_t RMASK = 3u << (2 * (K - 1) - 32);
     constexpr bool RARE = MINI && (K - M) >= 8 && (K - M) <= 16;                 // see score()
     constexpr uint32_t RTOP_LIMIT = (2 * M >= 32) ? (1u << (MINI ? 2 * M - 32 : 0)) : 1u;   // R < 4^M  <=>  top < RTOP_LIMIT
-    uint64_t f = 0, r = 0, s_k = 0, s_m = 0, pre = 0;
+    // scores of at most 32 bits (RARE shapes with M <= 16, e.g. k=21 m=11): the window minima are one VIMNMX each instead of
+    // DSETP + 2 SEL — 30 of the 41 64-bit minima per 11 bases
+    constexpr bool S32 = RARE && 2 * M <= 32;
+    // (FP64-pipe minima for the 42-bit scores of m = 21 — doubles 2^52 + x, min(a, c) = a - ((a - c) + |a - c|) / 2, three DADD / DFMA and no
+    //  INT-pipe instruction — measured 539 vs 551 Gbases/s on the headline shape: dropped)
+    using ScoreT = typename std::conditional<S32, uint32_t, uint64_t>::type;
+    uint64_t f = 0, r = 0, s_k = 0, s_m = 0;
+    ScoreT pre = 0;
     uint32_t seen = 0, n_nrc = 0, rtop_min = 0xFFFFFFFFu;
-    uint64_t buf[W + 1];
+    ScoreT buf[W + 1];
+    auto smin = [](ScoreT a, ScoreT c) -> ScoreT {
+        if constexpr (S32) return a < c ? a : c;
+        else return lt62(a, c) ? a : c;
+    };
 #pragma unroll
     for (int i = 0; i <= W; i++) buf[i] = 0;
     int p = ws;
@@ -584,22 +596,23 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
     // the smaller one when R < 4^M, i.e. when the last K-M bases are all T (4^-(K-M) per position in random sequence):
     // RARE shapes take x and only remember the smallest top part of R seen; an item where that ever reached zero
     // is handed to walk_fast like one with a non-ACGT base.
-    auto score = [&]() -> uint64_t {
-        const uint64_t x = f & MMASK;
-        if (RARE) {
+    auto score = [&]() -> ScoreT {
+        if constexpr (RARE) {
             const uint32_t top = (2 * M >= 32) ? (uint32_t)(r >> 32) : (uint32_t)(r >> (2 * M));
             rtop_min = top < rtop_min ? top : rtop_min;
-            return x;
+            if constexpr (S32) return (uint32_t)f & (uint32_t)MMASK;
+            else return f & MMASK;
+        } else {
+            const uint64_t x = f & MMASK, y = r | LMASK;
+            return lt62(x, y) ? x : y;
         }
-        const uint64_t y = r | LMASK;
-        return lt62(x, y) ? x : y;
     };
-    auto tally = [&](uint64_t win) {
+    auto tally = [&](ScoreT win) {
         const uint64_t fm = f & KMASK;
         const bool lt = lt62(fm, r);                 // ties => was_rc = true (kmer.rs:124-128)
         s_k += lt ? fm : r;
         n_nrc += lt ? 1u : 0u;
-        if (MINI) s_m += win;
+        if (MINI) s_m += (uint64_t)win;
     };
     // one rotated block: element W-1 of the running van Herk block, the suffix pass, elements 0..W-2 of the next block
     auto block = [&](auto check) {
@@ -608,19 +621,19 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
         for (int j = 0; j < B; j++) {
             if (CHECK && p + j >= b) return;
             roll(p + j);
-            uint64_t win = 0;
+            ScoreT win = 0;
             if (MINI) {
-                const uint64_t sc = score();
+                const ScoreT sc = score();
                 if (j == 0) {
-                    pre = (W == 1 || lt62(sc, pre)) ? sc : pre;
+                    pre = W == 1 ? sc : smin(sc, pre);
                     win = pre;
                     buf[W - 1] = sc;
 #pragma unroll
-                    for (int q = W - 2; q >= 1; q--) buf[q] = lt62(buf[q], buf[q + 1]) ? buf[q] : buf[q + 1];
+                    for (int q = W - 2; q >= 1; q--) buf[q] = smin(buf[q], buf[q + 1]);
                 } else {
                     const int i = j - 1;
-                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
-                    win = lt62(buf[i + 1], pre) ? buf[i + 1] : pre;
+                    pre = i == 0 ? sc : smin(sc, pre);
+                    win = smin(buf[i + 1], pre);
                     buf[i] = sc;
                 }
             }
@@ -638,8 +651,8 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
             r = (r >> 2) | ((uint64_t)((3u - code) << (2 * (K - 1) - 32)) << 32);
             if (MINI && h >= M - 1) {
                 const int i = h - (M - 1);
-                const uint64_t sc = score();
-                pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                const ScoreT sc = score();
+                pre = i == 0 ? sc : smin(sc, pre);
                 buf[i] = sc;
             }
         }
@@ -652,8 +665,8 @@ __host__ __device__ __forceinline__ bool walk_clean(const uint8_t* __restrict__ 
             for (int i = 0; i < W - 1; i++) {
                 if (p + i < b) {
                     roll(p + i);
-                    const uint64_t sc = score();
-                    pre = (i == 0 || lt62(sc, pre)) ? sc : pre;
+                    const ScoreT sc = score();
+                    pre = i == 0 ? sc : smin(sc, pre);
                     buf[i] = sc;
                 }
             }
