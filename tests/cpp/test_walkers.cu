@@ -76,7 +76,7 @@ static int run(std::mt19937_64& rng, int iters, const char* name) {
             if (flavour >= 1 && roll < (flavour == 3 ? 80u : 8u)) c = "NnRYKM-.~UuXx*"[(r >> 20) % 14];
             if (flavour >= 2 && roll >= 990) c = " \t\r"[(r >> 30) % 3];
         }
-        if (flavour == 4)                                     // runs of T: RC_k(x) < x happens (walk_clean's rare case)
+        if (flavour == 4 || (flavour == 1 && it % 2 == 0))    // runs of T: RC_k(x) < x happens (the rare case of walk_clean / walk_fast), also next to non-ACGT bases
             for (int q = 0; q < 3 && n > 0; q++) { const int at = (int)(rng() % (unsigned)n), len = 4 + (int)(rng() % 30); for (int j = at; j < n && j < at + len; j++) s[j] = (rng() & 1) ? 'T' : 't'; }
         // (a line never contains '\n'; the kernel strips one trailing '\r' itself)
         const uint8_t* sb = (const uint8_t*)s.data();
