@@ -374,7 +374,9 @@ def run_ours(args):
                 "kernel": "fqw::k_records (+ k_verify, fix-up launch)" if tallies.get("fast_path") else "fused::k_fused", "kernel_ms": kavg,
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "traffic_note": "DRAM bytes per launch = ncu dram read+write bytes per input byte (profiles/traffic.json) x algorithmic bytes",
-                "note": "single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~41 SASS thread-instructions per base, ~25 of them on the 16-lane INT pipe, which is 84 % busy in the record-owned kernel (ncu profiles/r2h_*; 63 % in the tile kernel it replaces for short-read FASTQ); see DESIGN.md"}
+                "note": ("single pass (DRAM traffic = 1.01 x algorithmic bytes) but integer-pipe bound, not HBM bound: ~41 SASS thread-instructions per base, ~25 of them on the 16-lane INT pipe, which is 84 % busy in the record-owned kernel (ncu profiles/r2h_*; 63 % in the tile kernel it replaces for short-read FASTQ); see DESIGN.md"
+                         if tallies.get("fast_path") else
+                         "single pass over the text (tile kernel: TMA-staged tiles, decoupled look-back) but integer-pipe bound, not HBM bound: the walker costs ~24 SASS instructions per base at k=21 m=11, ~31 at k=31 m=21; see DESIGN.md 3.1 / 6")}
 
     # ---- end to end through the host-facing C-ABI call: pinned host FASTQ -> H2D -> fused kernel -> tallies
     e2e = None
@@ -411,7 +413,7 @@ def run_ours(args):
             best = dt if best is None else min(best, dt)
         e2e = {"value": total_rec * L / best / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 192 * ((nbytes >> 26) + 1),
                "seconds": best, "host_buffer_bytes": hbytes, "calls_per_step": calls, "repeats": 2,
-               "note": "ntg_tally_fastx on pinned host FASTQ, streamed through three 64 MiB device segments (bounded device memory); PCIe H2D bound"}
+               "note": "ntg_tally_fastx on pinned host text, streamed through three 64 MiB device segments (bounded device memory); PCIe H2D bound"}
         ctx.lib.ntg_free_pinned(hp)
 
     cpu = None
