@@ -16,7 +16,8 @@
 // Grow-only device scratch of the materialising paths (record scanner): a context keeps its buffers between calls instead
 // of paying cudaMalloc / cudaFree (which synchronise the device) for ~6 buffers per window.  Calls on one context are serial.
 struct ScratchPool {
-    enum Slot { BYTES, COUNTS, NLPOS, STPOS, STORD, STCR, RECS, ERRKIND, MISC, SLOTS };
+    enum Slot { BYTES, COUNTS, NLPOS, STPOS, STORD, STCR, RECS, ERRKIND, MISC,                                  // record scanner
+                SQ_SEQS, SQ_OFFS, SQ_RC, SQ_FLAGS, SQ_IDX, SQ_TMP, SQ_OUT, SQ_CHG, SQ_LO, SQ_HI, SQ_OOFFS, SLOTS };  // Sequence batch calls
     void* dev[SLOTS] = {};
     size_t cap[SLOTS] = {};
     void* get(int slot, size_t bytes) {                  // nullptr: out of device memory
@@ -37,15 +38,17 @@ struct ScratchPool {
 // context and the tables it returned, so a table may outlive its context.
 struct PinPool {
     struct Ent { void* p; size_t cap; };
+    static constexpr size_t MAX_SPARE = 8;
     std::mutex mu;
     bool closed = false;
     std::vector<Ent> spare;
     void* take(size_t bytes, size_t* cap_out) {
         {
             std::lock_guard<std::mutex> g(mu);
+            size_t best = spare.size();
             for (size_t i = 0; i < spare.size(); i++)
-                if (spare[i].cap >= bytes) { Ent e = spare[i]; spare.erase(spare.begin() + i); *cap_out = e.cap; return e.p; }
-            if (!spare.empty()) { cudaFreeHost(spare.back().p); spare.pop_back(); }      // too small: replace it
+                if (spare[i].cap >= bytes && (best == spare.size() || spare[i].cap < spare[best].cap)) best = i;
+            if (best < spare.size()) { Ent e = spare[best]; spare.erase(spare.begin() + best); *cap_out = e.cap; return e.p; }
         }
         void* p = nullptr;
         const size_t want = bytes + bytes / 8 + 256;
@@ -55,7 +58,14 @@ struct PinPool {
     }
     void give(void* p, size_t cap) {
         std::lock_guard<std::mutex> g(mu);
-        if (closed || spare.size() >= 2) cudaFreeHost(p); else spare.push_back(Ent{p, cap});
+        if (closed) { cudaFreeHost(p); return; }
+        spare.push_back(Ent{p, cap});
+        if (spare.size() > MAX_SPARE) {                   // drop the smallest one
+            size_t w = 0;
+            for (size_t i = 1; i < spare.size(); i++) if (spare[i].cap < spare[w].cap) w = i;
+            cudaFreeHost(spare[w].p);
+            spare.erase(spare.begin() + w);
+        }
     }
     void close() {
         std::lock_guard<std::mutex> g(mu);
@@ -107,10 +117,17 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    bool owned = true;
+    ~DevBuf() { if (p && owned) cudaFree(p); }
     cudaError_t alloc(size_t count) {
         n = count;
         return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    }
+    // a slot of the context's grow-only scratch instead of an allocation of its own (nothing is freed here)
+    cudaError_t alloc_pooled(ScratchPool& pool, int slot, size_t count) {
+        n = count; owned = false;
+        p = static_cast<T*>(pool.get(slot, (count ? count : 1) * sizeof(T)));
+        return p ? cudaSuccess : cudaErrorMemoryAllocation;
     }
 };
 // RAII pinned host buffer
@@ -121,10 +138,17 @@ struct PinBuf {
     PinBuf() = default;
     PinBuf(const PinBuf&) = delete;
     PinBuf& operator=(const PinBuf&) = delete;
-    ~PinBuf() { if (p) cudaFreeHost(p); }
+    std::shared_ptr<PinPool> pool;        // set: the buffer came from (and goes back to) the context's pinned pool
+    size_t cap = 0;
+    ~PinBuf() { if (p) { if (pool) pool->give(p, cap); else cudaFreeHost(p); } }
     cudaError_t alloc(size_t count) {
         n = count;
         return cudaMallocHost((void**)&p, (count ? count : 1) * sizeof(T));
+    }
+    cudaError_t alloc_pooled(const std::shared_ptr<PinPool>& from, size_t count) {
+        n = count; pool = from;
+        p = static_cast<T*>(pool->take((count ? count : 1) * sizeof(T), &cap));
+        return p ? cudaSuccess : cudaErrorMemoryAllocation;
     }
     T* release() { T* q = p; p = nullptr; return q; }
 };

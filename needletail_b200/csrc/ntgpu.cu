@@ -209,7 +209,8 @@ static int run_bytemap(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* quals, 
         NTG_TRY(upload_batch(ctx, seqs + offs[a], sub.data(), e - a, b));
         if (b.total) {
             DevBuf<uint8_t> dq, dout;
-            if (dout.alloc(b.total) || (quals && dq.alloc(b.total))) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+            if (dout.alloc_pooled(ctx->scratch, ScratchPool::SQ_OUT, b.total) || (quals && dq.alloc_pooled(ctx->scratch, ScratchPool::SQ_RC, b.total)))
+                return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
             if (quals) {
                 NTG_CUDA(ctx, cudaMemcpyAsync(dq.p, quals + offs[a], b.total, cudaMemcpyHostToDevice, ctx->stream));
                 seqops::k_qmask<<<seqops::grid_for(b.total), seqops::BLOCK, 0, ctx->stream>>>(b.seqs.p, dq.p, b.total, (uint8_t)score, dout.p);

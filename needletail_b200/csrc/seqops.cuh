@@ -196,7 +196,7 @@ static int upload_batch(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs,
     if (total >= 0xFFFFFFF0ull || n >= 0xFFFFFFF0ull)
         return ntg_set_error(ctx, NTG_EUNSUPPORTED, "a single sequence of %llu bytes: sequences are limited to 4 GiB", (unsigned long long)total);
     b.nseq = (uint32_t)n; b.total = (uint32_t)total;
-    if (b.seqs.alloc(total) != cudaSuccess || b.offs.alloc(n + 1) != cudaSuccess)
+    if (b.seqs.alloc_pooled(ctx->scratch, ScratchPool::SQ_SEQS, total) != cudaSuccess || b.offs.alloc_pooled(ctx->scratch, ScratchPool::SQ_OFFS, n + 1) != cudaSuccess)
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     std::vector<uint32_t> o32(n + 1);
     for (size_t i = 0; i <= n; i++) o32[i] = (uint32_t)offs[i];
@@ -248,8 +248,10 @@ static int run_xform_one(ntg_ctx* ctx, const uint8_t* seqs, const uint64_t* offs
     BatchOnDevice b;
     NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
     DevBuf<uint8_t> keep, dout, dchg; DevBuf<uint32_t> idx, tmp; DevBuf<uint64_t> dooffs;
-    if (keep.alloc(b.total) || dout.alloc(b.total) || dchg.alloc(n) || idx.alloc((size_t)b.total + 1) ||
-        tmp.alloc(scan_tmp_count(b.total)) || dooffs.alloc(n + 1))
+    ScratchPool& sp = ctx->scratch;
+    if (keep.alloc_pooled(sp, ScratchPool::SQ_FLAGS, b.total) || dout.alloc_pooled(sp, ScratchPool::SQ_OUT, b.total) || dchg.alloc_pooled(sp, ScratchPool::SQ_CHG, n) ||
+        idx.alloc_pooled(sp, ScratchPool::SQ_IDX, (size_t)b.total + 1) || tmp.alloc_pooled(sp, ScratchPool::SQ_TMP, scan_tmp_count(b.total)) ||
+        dooffs.alloc_pooled(sp, ScratchPool::SQ_OOFFS, n + 1))
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     NTG_CUDA(ctx, cudaMemsetAsync(dchg.p, 0, n ? n : 1, ctx->stream));
     if (b.total) {
@@ -293,10 +295,12 @@ static int run_kmers_one(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, c
     NTG_TRY(upload_batch(ctx, seqs, offs, n, b));
     DevBuf<uint8_t> drc, valid, dwas; DevBuf<uint32_t> idx, tmp, dpos; DevBuf<uint64_t> dlo, dhi, dioffs;
     if (rc) {
-        if (drc.alloc(b.total)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
+        if (drc.alloc_pooled(ctx->scratch, ScratchPool::SQ_RC, b.total)) return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
         NTG_CUDA(ctx, cudaMemcpyAsync(drc.p, rc, b.total, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (valid.alloc(b.total) || idx.alloc((size_t)b.total + 1) || tmp.alloc(scan_tmp_count(b.total)) || dioffs.alloc(n + 1))
+    ScratchPool& sp = ctx->scratch;
+    if (valid.alloc_pooled(sp, ScratchPool::SQ_FLAGS, b.total) || idx.alloc_pooled(sp, ScratchPool::SQ_IDX, (size_t)b.total + 1) ||
+        tmp.alloc_pooled(sp, ScratchPool::SQ_TMP, scan_tmp_count(b.total)) || dioffs.alloc_pooled(sp, ScratchPool::SQ_OOFFS, n + 1))
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     if (b.total) {
         k_kmer_valid<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, b.offs.p, b.nseq, b.total, k, mode == 4 ? 1 : 0, valid.p);
@@ -310,7 +314,8 @@ static int run_kmers_one(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, c
     NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const bool want_val = mode != 4;
     bool want_hi = (mode == 0 && k > 32), want_rc = (mode != 3 && mode != 4);
-    if (dpos.alloc(n_items) || (want_val && dlo.alloc(n_items)) || (want_hi && dhi.alloc(n_items)) || dwas.alloc(n_items))
+    if (dpos.alloc_pooled(sp, ScratchPool::SQ_OUT, n_items) || (want_val && dlo.alloc_pooled(sp, ScratchPool::SQ_LO, n_items)) ||
+        (want_hi && dhi.alloc_pooled(sp, ScratchPool::SQ_HI, n_items)) || dwas.alloc_pooled(sp, ScratchPool::SQ_CHG, n_items))
         return ntg_set_error(ctx, NTG_ENOMEM, "device allocation failed");
     if (b.total && n_items) {
         k_kmer_emit<<<grid_for(b.total), BLOCK, 0, ctx->stream>>>(b.seqs.p, rc ? drc.p : nullptr, b.offs.p, b.nseq, b.total, k, m,
@@ -321,8 +326,8 @@ static int run_kmers_one(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, c
     auto* priv = new ItemsPriv();
     auto* it = new ntg_items();
     auto fail = [&](int st, const char* msg) { delete priv; delete it; return ntg_set_error(ctx, st, "%s", msg); };
-    if (priv->item_offs.alloc(n + 1) || priv->pos.alloc(n_items) || (want_val && priv->val_lo.alloc(n_items)) ||
-        (want_hi && priv->val_hi.alloc(n_items)) || (want_rc && priv->was_rc.alloc(n_items)))
+    if (priv->item_offs.alloc_pooled(ctx->pinpool, n + 1) || priv->pos.alloc_pooled(ctx->pinpool, n_items) || (want_val && priv->val_lo.alloc_pooled(ctx->pinpool, n_items)) ||
+        (want_hi && priv->val_hi.alloc_pooled(ctx->pinpool, n_items)) || (want_rc && priv->was_rc.alloc_pooled(ctx->pinpool, n_items)))
         return fail(NTG_ENOMEM, "pinned allocation failed");
     cudaError_t e = cudaMemcpyAsync(priv->item_offs.p, dioffs.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (!e && n_items) {
@@ -366,8 +371,8 @@ static int run_kmers(ntg_ctx* ctx, const uint8_t* seqs, const uint8_t* rc, const
     auto* priv = new ItemsPriv();
     auto* it = new ntg_items();
     const bool want_val = parts[0]->val_lo != nullptr, want_hi = parts[0]->val_hi != nullptr, want_rc = parts[0]->was_rc != nullptr;
-    if (priv->item_offs.alloc(n + 1) || priv->pos.alloc(n_items) || (want_val && priv->val_lo.alloc(n_items)) ||
-        (want_hi && priv->val_hi.alloc(n_items)) || (want_rc && priv->was_rc.alloc(n_items))) {
+    if (priv->item_offs.alloc_pooled(ctx->pinpool, n + 1) || priv->pos.alloc_pooled(ctx->pinpool, n_items) || (want_val && priv->val_lo.alloc_pooled(ctx->pinpool, n_items)) ||
+        (want_hi && priv->val_hi.alloc_pooled(ctx->pinpool, n_items)) || (want_rc && priv->was_rc.alloc_pooled(ctx->pinpool, n_items))) {
         delete priv; delete it; drop();
         return ntg_set_error(ctx, NTG_ENOMEM, "pinned allocation failed");
     }
