@@ -59,6 +59,9 @@ extern "C" {
     pub fn ntg_create(device: c_int, out: *mut *mut ntg_ctx) -> c_int;
     pub fn ntg_destroy(ctx: *mut ntg_ctx);
     pub fn ntg_last_error(ctx: *const ntg_ctx) -> *const c_char;
+    pub fn ntg_release_scratch(ctx: *mut ntg_ctx) -> c_int;
+    pub fn ntg_alloc_pinned(bytes: usize, out: *mut *mut core::ffi::c_void) -> c_int;
+    pub fn ntg_free_pinned(p: *mut core::ffi::c_void) -> c_int;
     pub fn ntg_parse_fastx_chunk(ctx: *mut ntg_ctx, bytes: *const u8, n: usize, format: c_int, at_eof: c_int,
                                  out: *mut *mut ntg_records, consumed: *mut u64) -> c_int;
     pub fn ntg_records_free(r: *mut ntg_records);

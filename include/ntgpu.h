@@ -65,6 +65,11 @@ int ntg_sync(ntg_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t ntg_launch_count(const ntg_ctx* ctx);
 
+/* The record scanner and the Sequence batch calls keep their device scratch and the pinned buffers of freed result tables between
+   calls (grow-only, sized by the largest window / batch seen so far: cudaMalloc / cudaMallocHost per call cost more than the work).
+   ntg_release_scratch hands all of it back to the driver; the next call allocates again.  ntg_destroy releases it too. */
+int ntg_release_scratch(ntg_ctx* ctx);
+
 /* pinned host memory for streaming feeds (cudaMemcpyAsync needs it to overlap) */
 int ntg_alloc_pinned(size_t bytes, void** out);
 int ntg_free_pinned(void* p);

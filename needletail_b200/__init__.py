@@ -98,6 +98,7 @@ def load_library():
         "ntg_device_info": ([vp, P(C.c_int), P(sz), P(C.c_int), P(C.c_int)], C.c_int),
         "ntg_sync": ([vp], C.c_int),
         "ntg_launch_count": ([vp], u64),
+        "ntg_release_scratch": ([vp], C.c_int),
         "ntg_alloc_pinned": ([sz, P(vp)], C.c_int),
         "ntg_free_pinned": ([vp], C.c_int),
         "ntg_device_alloc": ([vp, sz, P(u64)], C.c_int),
@@ -289,6 +290,10 @@ class Context:
         out = np.empty(max(1, n.value), dtype=np.uint8)
         self._ck(self.lib.ntg_write_records(*args, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value].tobytes()
+
+    def release_scratch(self):
+        """Hand the scanner's / batch calls' cached device scratch and pinned result buffers back — ntg_release_scratch"""
+        self._ck(self.lib.ntg_release_scratch(self.h))
 
     def parse_chunks(self, data, window=1 << 30, with_records=True):
         """Generator of Parsed, one per window of `window` bytes (< 4 GiB) — ntg_parse_fastx_chunk: the incremental reader behind

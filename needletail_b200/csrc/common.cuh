@@ -67,6 +67,11 @@ struct PinPool {
             spare.erase(spare.begin() + w);
         }
     }
+    void trim() {                                          // give the spare buffers back, keep serving
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& e : spare) cudaFreeHost(e.p);
+        spare.clear();
+    }
     void close() {
         std::lock_guard<std::mutex> g(mu);
         closed = true;

@@ -150,6 +150,13 @@ int ntg_memcpy_h2d(ntg_ctx* ctx, uint64_t dptr, const void* host, size_t bytes) 
     NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NTG_OK;
 }
+int ntg_release_scratch(ntg_ctx* ctx) {
+    CTX_ENTER(ctx);
+    NTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->scratch.release();
+    ctx->pinpool->trim();
+    return NTG_OK;
+}
 int ntg_memcpy_d2h(ntg_ctx* ctx, void* host, uint64_t dptr, size_t bytes) {
     CTX_ENTER(ctx);
     NTG_CUDA(ctx, cudaMemcpyAsync(host, (const void*)(uintptr_t)dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));

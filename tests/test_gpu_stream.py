@@ -308,3 +308,14 @@ def test_device_inflate_in_the_tally_session(ctx):
     ref = s.finish()
     same(got, ref, "device vs host inflate, multi-batch")
     assert one["n_records"] > 0
+
+
+def test_release_scratch_between_calls(ctx):  # ntg_release_scratch: the cached scratch can be handed back at any point
+    fq = O.gen_fastq(0x5EED0002, 0, 2000, 150, 0).tobytes()
+    exp = O.parse_fastx(fq)
+    for _ in range(2):
+        got = ctx.parse(fq)
+        assert len(got.records) == len(exp.records) and np.array_equal(got.table, exp.table[:, :10])
+        it = ctx.bit_kmers([fq[12:162]], 31, True)
+        assert len(it.pos) == 120
+        ctx.release_scratch()
