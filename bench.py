@@ -48,11 +48,16 @@ def load_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic_ratio():
-    """DRAM bytes per input byte of the fused kernel from the committed ncu --set full capture (or None)."""
+def load_traffic_ratio(kernel=None, fasta=False):
+    """DRAM bytes per input byte of the named kernel from the committed ncu --set full captures (or None)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_input_byte"])
+            t = json.load(f)
+        ks = t.get("kernels", {})
+        for key in ((kernel + " (FASTA, C3)") if (kernel and fasta) else None, kernel):
+            if key and key in ks:
+                return float(ks[key]["dram_bytes_per_input_byte"])
+        return float(t["dram_bytes_per_input_byte"])
     except Exception:
         return None
 
@@ -368,7 +373,8 @@ def run_ours(args):
     peak, peak_src = load_peak()
     kavg = sum(kernel_ms) / len(kernel_ms)
     achieved = nbytes / (kavg * 1e-3) / 1e9
-    ratio = load_traffic_ratio()
+    kname = "fqw::k_records" if tallies.get("fast_path") else "fused::k_fused"
+    ratio = load_traffic_ratio(kname, fasta=(fmt == "fasta"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (ratio * nbytes) if ratio else None,
                 "kernel": "fqw::k_records (+ k_verify, fix-up launch)" if tallies.get("fast_path") else "fused::k_fused", "kernel_ms": kavg,
